@@ -1,0 +1,60 @@
+"""ctypes binding of libpwclo_b200.so (the C ABI declared in include/pwclo_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a CUDA tensor is not
+supplied, the call raises.  A CPU or PyTorch-eager stand-in would void every parity claim.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpwclo_b200.so")
+_lib = None
+
+_vp, _i, _u, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_float
+
+# name -> argtypes  (must list every symbol declared in include/pwclo_b200.h; tests check this)
+SIGNATURES = {
+    "pwclo_furthest_point_sampling": [_vp, _i, _i, _i, _u, _vp, _vp],
+    "pwclo_gather_points": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "pwclo_gather_points_grad": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "pwclo_group_points": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "pwclo_group_points_grad": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "pwclo_ball_query": [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp],
+    "pwclo_three_nn": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "pwclo_three_interpolate": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "pwclo_three_interpolate_grad": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "pwclo_knn": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+}
+
+
+class PwcloError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PwcloError(
+                f"{LIB_PATH} is missing: build it with `python -m pwclonet_pylidarslam_b200.csrc.build` "
+                "(nvcc, sm_100a). There is no CPU / PyTorch fallback for this path.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = ctypes.c_int
+        L.pwclo_version.restype = ctypes.c_char_p
+        L.pwclo_error_string.restype = ctypes.c_char_p
+        L.pwclo_error_string.argtypes = [ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        raise PwcloError(f"{what} failed: {lib().pwclo_error_string(code).decode()} (code {code})")
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,173 @@
+// Brute-force k-nearest-neighbour search for sm_100a -- replaces the reference's pure-PyTorch
+// `knn_point` (P2/pytorch_utils.py:12-49), which materialises [B,S,N,3] differences (~2 GB of HBM
+// traffic per 8192-point cloud) and runs torch.topk.
+//
+// Design:
+//   * the reference set of one cloud is staged once per CTA in shared memory as SoA tiles
+//     (<= 8192 points = 96 KB) and re-used by every query the CTA owns; HBM/L2 traffic is the
+//     compulsory 12 B/point per CTA instead of 12 B per (query, point) pair;
+//   * one warp owns Q queries at a time; per 32-reference chunk each lane evaluates Q distances
+//     from one shared-memory read of the reference point (register tiling over queries);
+//   * selection: the running top-K of a query is a warp-distributed sorted list (lane i holds the
+//     i-th best).  A candidate is first tested against the K-th squared distance (cheap, no sqrt);
+//     survivors (O(K log(N/K)) per query) are inserted with ballot + shfl_up;
+//   * the compared quantity is bit-for-bit the reference's: unfused fp32 (q-r)^2 products, the
+//     size-3 sum in torch's order (selectable), + 1e-8f, IEEE sqrt; equal distances are ordered by
+//     index (torch.topk leaves that order unspecified);
+//   * optional fused pose warp of the queries (PW/PWCLO_utils.py:42-63), so the warped cloud of a
+//     refinement level never makes a round trip through HBM before its neighbour search.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace pwclo {
+
+constexpr int KNN_WARPS = 8;       // warps per CTA
+constexpr int KNN_MAX_TILE = 8192;  // reference points per shared-memory tile
+
+template <int Q, int SUM_ORDER>
+__global__ void __launch_bounds__(KNN_WARPS * 32)
+knn_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int N, int S, int K, int tile,
+           int q_per_cta, const float* __restrict__ warp_qt, float* __restrict__ warped_out,
+           int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+  extern __shared__ float smem[];
+  float* sx = smem;
+  float* sy = sx + tile;
+  float* sz = sy + tile;
+
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  xyz += (size_t)b * N * 3;
+  new_xyz += (size_t)b * S * 3;
+  const int q_begin = blockIdx.x * q_per_cta;
+  const int q_end = min(S, q_begin + q_per_cta);
+
+  PoseQT pose;
+  const bool do_warp = warp_qt != nullptr;
+  if (do_warp) pose = make_pose(warp_qt + (size_t)b * 7);
+
+  // a cloud that fits one tile is staged exactly once per CTA
+  const bool single_tile = N <= tile;
+  if (single_tile) {
+    for (int i = threadIdx.x; i < N; i += KNN_WARPS * 32) {
+      sx[i] = xyz[i * 3 + 0];
+      sy[i] = xyz[i * 3 + 1];
+      sz[i] = xyz[i * 3 + 2];
+    }
+    __syncthreads();
+  }
+
+  // the CTA's queries are processed in rounds of KNN_WARPS*Q; every round walks all reference tiles.
+  for (int q0 = q_begin; q0 < q_end; q0 += KNN_WARPS * Q) {
+    float qx[Q], qy[Q], qz[Q];
+    float lv[Q], ld[Q], kth_v[Q], thr_d[Q];
+    int li[Q];
+    int qi[Q];
+#pragma unroll
+    for (int u = 0; u < Q; ++u) {
+      qi[u] = q0 + warp * Q + u;
+      int qq = min(qi[u], S - 1);
+      float x = new_xyz[qq * 3 + 0], y = new_xyz[qq * 3 + 1], z = new_xyz[qq * 3 + 2];
+      if (do_warp) {
+        warp_point(pose, x, y, z, x, y, z);
+        if (warped_out != nullptr && lane == 0 && qi[u] < q_end) {
+          float* w = warped_out + ((size_t)b * S + qq) * 3;
+          w[0] = x; w[1] = y; w[2] = z;
+        }
+      }
+      qx[u] = x; qy[u] = y; qz[u] = z;
+      lv[u] = CUDART_INF_F; ld[u] = CUDART_INF_F; li[u] = 0;
+      kth_v[u] = CUDART_INF_F; thr_d[u] = CUDART_INF_F;
+    }
+
+    for (int t0 = 0; t0 < N; t0 += tile) {
+      const int tn = min(tile, N - t0);
+      if (!single_tile) {
+        __syncthreads();  // previous tile / round fully consumed
+        for (int i = threadIdx.x; i < tn; i += KNN_WARPS * 32) {
+          sx[i] = xyz[(t0 + i) * 3 + 0];
+          sy[i] = xyz[(t0 + i) * 3 + 1];
+          sz[i] = xyz[(t0 + i) * 3 + 2];
+        }
+        __syncthreads();
+      }
+
+      for (int c0 = 0; c0 < tn; c0 += 32) {
+        const int r = c0 + lane;
+        const bool rv = r < tn;
+        const float rx = rv ? sx[r] : 0.f, ry = rv ? sy[r] : 0.f, rz = rv ? sz[r] : 0.f;
+#pragma unroll
+        for (int u = 0; u < Q; ++u) {
+          const float dx = __fsub_rn(qx[u], rx), dy = __fsub_rn(qy[u], ry), dz = __fsub_rn(qz[u], rz);
+          const float xx = __fmul_rn(dx, dx), yy = __fmul_rn(dy, dy), zz = __fmul_rn(dz, dz);
+          const float d2 = SUM_ORDER == 0 ? __fadd_rn(__fadd_rn(xx, yy), zz) : __fadd_rn(__fadd_rn(xx, zz), yy);
+          unsigned mask = __ballot_sync(PWCLO_FULL_MASK, rv && d2 <= thr_d[u]);
+          while (mask) {  // warp-uniform
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float cd = __shfl_sync(PWCLO_FULL_MASK, d2, src);
+            if (cd > thr_d[u]) continue;
+            const float cv = __fsqrt_rn(__fadd_rn(cd, 1e-8f));
+            if (!(cv < kth_v[u])) continue;  // equal distance, higher index: loses the tie
+            const int pos = __popc(__ballot_sync(PWCLO_FULL_MASK, lv[u] <= cv));
+            const float pv = __shfl_up_sync(PWCLO_FULL_MASK, lv[u], 1);
+            const float pd = __shfl_up_sync(PWCLO_FULL_MASK, ld[u], 1);
+            const int pi = __shfl_up_sync(PWCLO_FULL_MASK, li[u], 1);
+            if (lane > pos) { lv[u] = pv; ld[u] = pd; li[u] = pi; }
+            else if (lane == pos) { lv[u] = cv; ld[u] = cd; li[u] = t0 + c0 + src; }
+            kth_v[u] = __shfl_sync(PWCLO_FULL_MASK, lv[u], K - 1);
+            thr_d[u] = __shfl_sync(PWCLO_FULL_MASK, ld[u], K - 1);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < Q; ++u) {
+      if (qi[u] < q_end && lane < K) {
+        size_t o = ((size_t)b * S + qi[u]) * K + lane;
+        idx_out[o] = li[u];
+        if (dist_out) dist_out[o] = lv[u];
+      }
+    }
+  }
+}
+
+template <int Q>
+static int launch_knn(const float* xyz, const float* new_xyz, int B, int N, int S, int K, int sum_order,
+                      const float* warp_qt, float* warped_out, int32_t* idx, float* dist, cudaStream_t st) {
+  const int tile = min(((N + 31) / 32) * 32, KNN_MAX_TILE);
+  const size_t smem = (size_t)3 * tile * sizeof(float);
+  // queries per CTA: enough CTAs to fill the machine (>= 2 waves of 148 SMs x resident CTAs) while
+  // amortising the shared-memory fill of the reference tile over as many queries as possible.
+  const int per_round = KNN_WARPS * Q;
+  int q_per_cta = per_round;
+  const int resident = smem > 64 * 1024 ? 2 : 4;
+  while (q_per_cta * 2 <= S && (long long)B * ceil_div(S, q_per_cta * 2) >= 2LL * kNumSM * resident) q_per_cta *= 2;
+  dim3 grid(ceil_div(S, q_per_cta), B);
+  auto kern = sum_order == PWCLO_KNN_SUM_XY_Z ? knn_kernel<Q, 0> : knn_kernel<Q, 1>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  kern<<<grid, KNN_WARPS * 32, smem, st>>>(xyz, new_xyz, N, S, K, tile, q_per_cta, warp_qt, warped_out, idx, dist);
+  return launch_status();
+}
+
+}  // namespace pwclo
+
+using namespace pwclo;
+
+PWCLO_API int pwclo_knn(const float* xyz, const float* new_xyz, int B, int N, int S, int K, int sum_order,
+                        const float* warp_qt, float* warped_out, int32_t* idx, float* dist, void* stream) {
+  if (!xyz || !new_xyz || !idx || B < 0 || N <= 0 || S < 0 || K <= 0) return PWCLO_EINVAL;
+  if (K > 32) return PWCLO_EUNSUPPORTED;   // the reference never asks for more than 32 neighbours
+  if (K > N) return PWCLO_EINVAL;          // torch.topk raises in the reference
+  if (sum_order != PWCLO_KNN_SUM_XY_Z && sum_order != PWCLO_KNN_SUM_XZ_Y) return PWCLO_EINVAL;
+  if (B == 0 || S == 0) return PWCLO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((long long)B * S >= 4LL * kNumSM * KNN_WARPS * 4)
+    return launch_knn<4>(xyz, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist, st);
+  if ((long long)B * S >= 4LL * kNumSM * KNN_WARPS * 2)
+    return launch_knn<2>(xyz, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist, st);
+  return launch_knn<1>(xyz, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist, st);
+}
