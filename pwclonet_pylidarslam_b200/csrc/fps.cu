@@ -137,7 +137,7 @@ static int launch_fps(const float* xyz, int B, int n, int m, int logT, int origi
                       cudaStream_t st) {
   size_t smem = MODE == 2 ? 0 : (size_t)3 * n * sizeof(float);
   auto kern = fps_kernel<P, THREADS, MODE>;
-  if (smem > 48 * 1024) {
+  if (smem > 32 * 1024) {  // static smem (reduction slots) counts against the 48 KB default limit
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }

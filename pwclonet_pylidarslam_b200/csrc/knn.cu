@@ -8,9 +8,11 @@
 //     compulsory 12 B/point per CTA instead of 12 B per (query, point) pair;
 //   * one warp owns Q queries at a time; per 32-reference chunk each lane evaluates Q distances
 //     from one shared-memory read of the reference point (register tiling over queries);
-//   * selection: the running top-K of a query is a warp-distributed sorted list (lane i holds the
-//     i-th best).  A candidate is first tested against the K-th squared distance (cheap, no sqrt);
-//     survivors (O(K log(N/K)) per query) are inserted with ballot + shfl_up;
+//   * selection (warp-select): the running top-K of a query is a warp-distributed sorted list (lane i
+//     holds the i-th best).  A candidate is first tested against a conservative squared-distance
+//     bound of the K-th entry (no sqrt); survivors (O(K log(N/K)) per query) are appended to a small
+//     shared-memory queue and merged 32 at a time with a warp bitonic sort + merge on 64-bit
+//     (distance, index) keys;
 //   * the compared quantity is bit-for-bit the reference's: unfused fp32 (q-r)^2 products, the
 //     size-3 sum in torch's order (selectable), + 1e-8f, IEEE sqrt; equal distances are ordered by
 //     index (torch.topk leaves that order unspecified);
@@ -22,8 +24,56 @@
 
 namespace pwclo {
 
-constexpr int KNN_WARPS = 8;       // warps per CTA
+constexpr int KNN_WARPS = 16;       // warps per CTA
 constexpr int KNN_MAX_TILE = 8192;  // reference points per shared-memory tile
+constexpr int KNN_BUF = 64;         // pending-candidate slots per (warp, query)
+
+typedef unsigned long long u64;
+constexpr u64 KNN_INF_KEY = 0x7f800000ffffffffull;
+
+// (distance, index) packed so that integer order == (distance asc, index asc); distances are >= 0
+__device__ __forceinline__ u64 knn_key(float v, int i) { return ((u64)__float_as_uint(v) << 32) | (unsigned)i; }
+
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m) {
+  unsigned lo = __shfl_xor_sync(PWCLO_FULL_MASK, (unsigned)v, m);
+  unsigned hi = __shfl_xor_sync(PWCLO_FULL_MASK, (unsigned)(v >> 32), m);
+  return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
+  unsigned lo = __shfl_sync(PWCLO_FULL_MASK, (unsigned)v, src);
+  unsigned hi = __shfl_sync(PWCLO_FULL_MASK, (unsigned)(v >> 32), src);
+  return ((u64)hi << 32) | lo;
+}
+
+// Merge up to 32 unsorted candidate keys (one per lane, KNN_INF_KEY = empty) into the sorted
+// 32-entry list (lane i = i-th smallest).  Bitonic sort of the candidates (descending, 15
+// compare-exchange steps) + bitonic merge (1 + 5 steps): ~170 instructions per 32 candidates instead
+// of ~30 per candidate for one-at-a-time insertion.
+__device__ __noinline__ u64 knn_merge32(u64 list, u64 cand, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const u64 other = shfl_xor_u64(cand, j);
+      const bool desc_block = (lane & k) == 0 || k == 32;   // final pass: whole warp descending
+      const bool lower = (lane & j) == 0;
+      const bool keep_max = lower == desc_block;
+      cand = keep_max ? (cand > other ? cand : other) : (cand < other ? cand : other);
+    }
+  }
+  // list ascending, cand descending: element-wise min is a bitonic sequence holding the 32 smallest
+  u64 c = list < cand ? list : cand;
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const u64 other = shfl_xor_u64(c, j);
+    const bool lower = (lane & j) == 0;
+    c = lower ? (c < other ? c : other) : (c > other ? c : other);
+  }
+  return c;
+}
+
+// Conservative squared-distance bound: d2 > bound  =>  sqrt_rn(d2 + 1e-8f) >= kth  
+__device__ __forceinline__ float knn_bound(float kth) { return __fmul_ru(__fmul_ru(kth, kth), 1.0000005f); }
 
 template <int Q, int SUM_ORDER>
 __global__ void __launch_bounds__(KNN_WARPS * 32)
@@ -34,9 +84,11 @@ knn_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int
   float* sx = smem;
   float* sy = sx + tile;
   float* sz = sy + tile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* cand_d = sz + tile + (size_t)warp * Q * KNN_BUF;                                        // [Q][KNN_BUF]
+  int* cand_i = reinterpret_cast<int*>(sz + tile + (size_t)KNN_WARPS * Q * KNN_BUF) + (size_t)warp * Q * KNN_BUF;
 
   const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   xyz += (size_t)b * N * 3;
   new_xyz += (size_t)b * S * 3;
   const int q_begin = blockIdx.x * q_per_cta;
@@ -59,10 +111,9 @@ knn_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int
 
   // the CTA's queries are processed in rounds of KNN_WARPS*Q; every round walks all reference tiles.
   for (int q0 = q_begin; q0 < q_end; q0 += KNN_WARPS * Q) {
-    float qx[Q], qy[Q], qz[Q];
-    float lv[Q], ld[Q], kth_v[Q], thr_d[Q];
-    int li[Q];
-    int qi[Q];
+    float qx[Q], qy[Q], qz[Q], bound[Q];
+    u64 list[Q];
+    int cnt[Q], qi[Q];
 #pragma unroll
     for (int u = 0; u < Q; ++u) {
       qi[u] = q0 + warp * Q + u;
@@ -76,8 +127,9 @@ knn_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int
         }
       }
       qx[u] = x; qy[u] = y; qz[u] = z;
-      lv[u] = CUDART_INF_F; ld[u] = CUDART_INF_F; li[u] = 0;
-      kth_v[u] = CUDART_INF_F; thr_d[u] = CUDART_INF_F;
+      list[u] = KNN_INF_KEY;
+      bound[u] = CUDART_INF_F;
+      cnt[u] = 0;
     }
 
     for (int t0 = 0; t0 < N; t0 += tile) {
@@ -101,32 +153,48 @@ knn_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int
           const float dx = __fsub_rn(qx[u], rx), dy = __fsub_rn(qy[u], ry), dz = __fsub_rn(qz[u], rz);
           const float xx = __fmul_rn(dx, dx), yy = __fmul_rn(dy, dy), zz = __fmul_rn(dz, dz);
           const float d2 = SUM_ORDER == 0 ? __fadd_rn(__fadd_rn(xx, yy), zz) : __fadd_rn(__fadd_rn(xx, zz), yy);
-          unsigned mask = __ballot_sync(PWCLO_FULL_MASK, rv && d2 <= thr_d[u]);
-          while (mask) {  // warp-uniform
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float cd = __shfl_sync(PWCLO_FULL_MASK, d2, src);
-            if (cd > thr_d[u]) continue;
-            const float cv = __fsqrt_rn(__fadd_rn(cd, 1e-8f));
-            if (!(cv < kth_v[u])) continue;  // equal distance, higher index: loses the tie
-            const int pos = __popc(__ballot_sync(PWCLO_FULL_MASK, lv[u] <= cv));
-            const float pv = __shfl_up_sync(PWCLO_FULL_MASK, lv[u], 1);
-            const float pd = __shfl_up_sync(PWCLO_FULL_MASK, ld[u], 1);
-            const int pi = __shfl_up_sync(PWCLO_FULL_MASK, li[u], 1);
-            if (lane > pos) { lv[u] = pv; ld[u] = pd; li[u] = pi; }
-            else if (lane == pos) { lv[u] = cv; ld[u] = cd; li[u] = t0 + c0 + src; }
-            kth_v[u] = __shfl_sync(PWCLO_FULL_MASK, lv[u], K - 1);
-            thr_d[u] = __shfl_sync(PWCLO_FULL_MASK, ld[u], K - 1);
+          const bool pass = rv && d2 <= bound[u];
+          const unsigned mask = __ballot_sync(PWCLO_FULL_MASK, pass);
+          if (mask) {  // warp-uniform
+            float* cd = cand_d + u * KNN_BUF;
+            int* ci = cand_i + u * KNN_BUF;
+            if (pass) {
+              const int slot = cnt[u] + __popc(mask & ((1u << lane) - 1u));
+              cd[slot] = d2;
+              ci[slot] = t0 + r;
+            }
+            cnt[u] += __popc(mask);
+            if (cnt[u] >= 32) {
+              __syncwarp();
+              const u64 ck = knn_key(__fsqrt_rn(__fadd_rn(cd[lane], 1e-8f)), ci[lane]);
+              const int rest = cnt[u] - 32;
+              float md = 0.f; int mi = 0;
+              if (lane < rest) { md = cd[32 + lane]; mi = ci[32 + lane]; }
+              __syncwarp();
+              if (lane < rest) { cd[lane] = md; ci[lane] = mi; }
+              cnt[u] = rest;
+              list[u] = knn_merge32(list[u], ck, lane);
+              const float kth = __uint_as_float((unsigned)(shfl_u64(list[u], K - 1) >> 32));
+              bound[u] = knn_bound(kth);
+            }
           }
         }
       }
     }
 #pragma unroll
     for (int u = 0; u < Q; ++u) {
+      if (cnt[u] > 0) {   // warp-uniform: drain the pending candidates
+        __syncwarp();
+        const float* cd = cand_d + u * KNN_BUF;
+        const int* ci = cand_i + u * KNN_BUF;
+        const u64 ck = lane < cnt[u] ? knn_key(__fsqrt_rn(__fadd_rn(cd[lane], 1e-8f)), ci[lane]) : KNN_INF_KEY;
+        list[u] = knn_merge32(list[u], ck, lane);
+      }
+      __syncwarp();
       if (qi[u] < q_end && lane < K) {
         size_t o = ((size_t)b * S + qi[u]) * K + lane;
-        idx_out[o] = li[u];
-        if (dist_out) dist_out[o] = lv[u];
+        idx_out[o] = (int)(unsigned)list[u];
+        if (dist_out) dist_out[o] = __uint_as_float((unsigned)(list[u] >> 32));
       }
     }
   }
@@ -136,16 +204,16 @@ template <int Q>
 static int launch_knn(const float* xyz, const float* new_xyz, int B, int N, int S, int K, int sum_order,
                       const float* warp_qt, float* warped_out, int32_t* idx, float* dist, cudaStream_t st) {
   const int tile = min(((N + 31) / 32) * 32, KNN_MAX_TILE);
-  const size_t smem = (size_t)3 * tile * sizeof(float);
+  const size_t smem = (size_t)3 * tile * sizeof(float) + (size_t)KNN_WARPS * Q * KNN_BUF * 8;
   // queries per CTA: enough CTAs to fill the machine (>= 2 waves of 148 SMs x resident CTAs) while
   // amortising the shared-memory fill of the reference tile over as many queries as possible.
   const int per_round = KNN_WARPS * Q;
   int q_per_cta = per_round;
-  const int resident = smem > 64 * 1024 ? 2 : 4;
+  const int resident = smem > 110 * 1024 ? 1 : (smem > 72 * 1024 ? 2 : 3);
   while (q_per_cta * 2 <= S && (long long)B * ceil_div(S, q_per_cta * 2) >= 2LL * kNumSM * resident) q_per_cta *= 2;
   dim3 grid(ceil_div(S, q_per_cta), B);
   auto kern = sum_order == PWCLO_KNN_SUM_XY_Z ? knn_kernel<Q, 0> : knn_kernel<Q, 1>;
-  if (smem > 48 * 1024) {
+  if (smem > 32 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
@@ -164,10 +232,13 @@ PWCLO_API int pwclo_knn(const float* xyz, const float* new_xyz, int B, int N, in
   if (K > N) return PWCLO_EINVAL;          // torch.topk raises in the reference
   if (sum_order != PWCLO_KNN_SUM_XY_Z && sum_order != PWCLO_KNN_SUM_XZ_Y) return PWCLO_EINVAL;
   if (B == 0 || S == 0) return PWCLO_OK;
+  if (B > 65535) return PWCLO_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  if ((long long)B * S >= 4LL * kNumSM * KNN_WARPS * 4)
+  // queries per warp: as many as still leave >= 2 CTAs per SM
+  const long long total = (long long)B * S;
+  if (total >= 2LL * kNumSM * KNN_WARPS * 4)
     return launch_knn<4>(xyz, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist, st);
-  if ((long long)B * S >= 4LL * kNumSM * KNN_WARPS * 2)
+  if (total >= 2LL * kNumSM * KNN_WARPS * 2)
     return launch_knn<2>(xyz, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist, st);
   return launch_knn<1>(xyz, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist, st);
 }
