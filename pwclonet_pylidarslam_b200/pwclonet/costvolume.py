@@ -1,0 +1,50 @@
+"""Attentive point-to-patch cost volume, reference PW/costvolume.py:19-190 (same constructor,
+parameter names and forward signature).  This is the autograd / training composition on top of the
+sm_100a kNN + grouping kernels; inference goes through pwclonet_pylidarslam_b200.fused."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import pointnet2_utils as pointutils
+from .. import pytorch_utils as pt_utils
+
+
+class CostVolume(nn.Module):
+    def __init__(self, nsample, nsample_q, in_channel1, in_channel2, mlp1, mlp2):
+        super().__init__()
+        self.nsample, self.nsample_q = nsample, nsample_q
+        self.in_channel = [in_channel1, in_channel2, 10]
+        xu = torch.nn.init.xavier_uniform_
+        self.mlp_convs = pt_utils.SharedMLP([in_channel1 + in_channel2 + 10] + list(mlp1), bn=True, init=xu)
+        self.mlp_conv_xyz_1 = pt_utils.SharedMLP([10, mlp1[-1]], bn=True, init=xu)
+        self.mlp_conv_xyz_2 = pt_utils.SharedMLP([10, mlp1[-1]], bn=True, init=xu)
+        self.mlp2_convs = pt_utils.SharedMLP([mlp1[-1] * 2] + list(mlp2), bn=True, init=xu)
+        self.mlp3_convs = pt_utils.SharedMLP([mlp1[-1] * 2 + in_channel1] + list(mlp2), bn=True, init=xu)
+        self.out_channel = mlp2[-1]
+
+    @staticmethod
+    def _geometry(center, grouped):
+        """10 channels (p, q, q-p, |q-p|) of costvolume.py:94-105 / :159-169"""
+        k = grouped.size(3)
+        p = center.unsqueeze(3).expand(-1, -1, -1, k)
+        d = grouped - p
+        euc = torch.sqrt(torch.sum(torch.square(d), dim=1, keepdim=True) + 1e-20)
+        return torch.cat((p, grouped, d, euc), dim=1)
+
+    def forward(self, warped_xyz, warped_points, f2_xyz, f2_points):
+        """warped_xyz (B,3,S), warped_points (B,C,S), f2_xyz (B,3,N), f2_points (B,C,N) -> (B,mlp[-1],S)"""
+        w_t = warped_xyz.permute(0, 2, 1).contiguous()
+        f2_t = f2_xyz.permute(0, 2, 1).contiguous()
+        _, idx_q = pt_utils.knn_point(self.nsample_q, f2_t, w_t)
+        geo = self._geometry(warped_xyz, pointutils.grouping_operation(f2_xyz.contiguous(), idx_q))
+        p_f = warped_points.unsqueeze(3).expand(-1, -1, -1, self.nsample_q)
+        x = torch.cat((geo, p_f, pointutils.grouping_operation(f2_points.contiguous(), idx_q)), dim=1)
+        x = self.mlp_convs(x)
+        wq = F.softmax(self.mlp2_convs(torch.cat((self.mlp_conv_xyz_1(geo), x), dim=1)), dim=3)
+        e1 = torch.sum(wq * x, dim=3)
+        _, idx = pt_utils.knn_point(self.nsample, w_t, w_t)
+        c_e = pointutils.grouping_operation(e1.contiguous(), idx)
+        geo2 = self._geometry(warped_xyz, pointutils.grouping_operation(warped_xyz.contiguous(), idx))
+        n_f = warped_points.unsqueeze(3).expand(-1, -1, -1, self.nsample)
+        wp = F.softmax(self.mlp3_convs(torch.cat((self.mlp_conv_xyz_2(geo2), n_f, c_e), dim=1)), dim=3)
+        return torch.sum(wp * c_e, dim=3)
