@@ -7,7 +7,7 @@
  *     `_host`; tensors are dense, row-major, fp32 values / int32 indices;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); work is
  *     enqueued asynchronously, nothing synchronises, nothing allocates (callers own outputs and
- *     workspaces);
+ *     workspaces; the one exception is FPS with N > 16384, which takes a stream-ordered temporary);
  *   - return value: 0 on success, a positive cudaError_t if a launch failed, or a negative
  *     PWCLO_E* code for argument errors.  Nothing ever calls exit() (the reference's
  *     CUDA_CHECK_ERRORS macro does: _ext-src/include/cuda_utils.h:30-39).
@@ -88,6 +88,67 @@ int pwclo_three_interpolate_grad(const float *grad_out, const int32_t *idx, cons
  * (if warped_out != NULL) the transformed queries are written to warped_out[B,S,3]. */
 int pwclo_knn(const float *xyz, const float *new_xyz, int B, int N, int S, int K, int sum_order,
               const float *warp_qt, float *warped_out, int32_t *idx, float *dist, void *stream);
+
+/* ---- B2: fused inference layers (BatchNorm folded by the host side) ------------------------------
+ * Feature tensors are POINT-MAJOR [B,N,C] fp32 (the reference keeps [B,C,N]; pwclo_transpose
+ * converts), coordinates [B,N,3], neighbour indices [B,S,K] int32.
+ *
+ * pwclo_layer_t: one folded 1x1 convolution  y = relu(W x + b).
+ *   w: [cout/CB][k4][CB] fp32, CB = min(cout,64), k4 = (cin+3)&~3, rows k >= cin zero; i.e. column
+ *      blocks of 64 outputs, each stored k-major (input channel major).  16-byte aligned.
+ *   b: [cout] fp32, 16-byte aligned.  cout must be 8, 16, 32 or a multiple of 64.
+ * The order of the input channels (k) is the kernel's internal concat order, stated per function.
+ */
+typedef struct {
+  const float *w;
+  const float *b;
+  int cin;
+  int cout;
+} pwclo_layer_t;
+
+/* set conv (PointnetSAModulePWCLONet.forward, P2/pointnet2_modules.py:208-243) and the grouped half
+ * of set upconv (PointnetFPModulePWCLONet.forward, :480-506):
+ *   out[b,s,:] = max_k MLP([feats[b,idx[b,s,k],:] (C) | xyz[b,idx[b,s,k]] - new_xyz[b,s] (3)])
+ * feats == NULL: the neighbour's absolute xyz takes the place of the features (C = 3, level 1).
+ * layers[0].cin = C + 3 with input order (features, xyz_diff); 2 or 3 layers. */
+int pwclo_set_conv(const float *xyz, const float *feats, const float *new_xyz, const int32_t *idx,
+                   int B, int N, int S, int K, int C, const pwclo_layer_t *layers, int nlayers,
+                   float *out, void *stream);
+
+/* shared MLP on the channel concatenation of up to 3 point-major tensors with `rows` rows
+ * (FlowPredictor.forward, PW/flowpredictor.py:53-84; post_mlp of set upconv): 1 or 2 layers. */
+int pwclo_pointwise_mlp(const float *const *src, const int *channels, int nsrc, int rows,
+                        const pwclo_layer_t *layers, int nlayers, float *out, void *stream);
+
+/* CostVolume.forward first aggregation (PW/costvolume.py:75-144): out[B,S,64].
+ * mlp1[0] input order: (geo(10), 0, 0, f1(C), f2_grouped(C)) = 2C+12 rows; enc input (geo(10),0,0);
+ * geo = (p, q, q-p, |q-p|); mlp2[0] input (enc(64), mlp1_out(64)). */
+int pwclo_cost_volume_1(const float *wxyz, const float *f1, const float *xyz2, const float *f2,
+                        const int32_t *idx, int B, int S, int N, int K, int C,
+                        const pwclo_layer_t *mlp1 /*3*/, const pwclo_layer_t *enc,
+                        const pwclo_layer_t *mlp2 /*2*/, float *out, void *stream);
+
+/* CostVolume.forward second aggregation (PW/costvolume.py:150-188): out[B,S,64].
+ * mlp3[0] input order: (enc2(64), f1(C), e1_grouped(64)). */
+int pwclo_cost_volume_2(const float *wxyz, const float *f1, const float *e1, const int32_t *idx,
+                        int B, int S, int K, int C, const pwclo_layer_t *enc,
+                        const pwclo_layer_t *mlp3 /*2*/, float *out, void *stream);
+
+/* softmax over points of `mask`, PoseCalculator (PW/pose_calculator.py:47-87), composition with the
+ * coarse pose (PW/pose_warp_refinement.py:139,148; coarse_qt == NULL at the coarsest level) and the
+ * row `level` (0 = finest) of pose_params[B,4,7] = (t, q/|q|) (PW/pwclo_net.py:195-205).
+ * wqt [256,64], wq [4,256], wt [3,256] row-major (plain Conv1d weights), qt_out [B,7] = (q, t). */
+int pwclo_pose_head(const float *emb, const float *mask, int B, int S, const float *wqt,
+                    const float *bqt, const float *wq, const float *bq, const float *wt,
+                    const float *bt, const float *coarse_qt, float *qt_out, float *pose_params,
+                    int level, void *stream);
+
+/* out[b,j,:] = xyz[b,idx[b,j],:]  (gather_operation on [B,N,3], P2/pointnet2_modules.py:200-206) */
+int pwclo_gather_rows3(const float *xyz, const int32_t *idx, int B, int N, int M, float *out,
+                       void *stream);
+/* [B,C,N] -> [B,N,C] (to_point_major != 0) or back */
+int pwclo_transpose(const float *in, int B, int C, int N, int to_point_major, float *out,
+                    void *stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,14 @@ _lib = None
 
 _vp, _i, _u, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_float
 
+
+class LayerT(ctypes.Structure):
+    """pwclo_layer_t of include/pwclo_b200.h"""
+    _fields_ = [("w", ctypes.c_void_p), ("b", ctypes.c_void_p), ("cin", ctypes.c_int), ("cout", ctypes.c_int)]
+
+
+_LP = ctypes.POINTER(LayerT)
+
 # name -> argtypes  (must list every symbol declared in include/pwclo_b200.h; tests check this)
 SIGNATURES = {
     "pwclo_furthest_point_sampling": [_vp, _i, _i, _i, _u, _vp, _vp],
@@ -24,6 +32,13 @@ SIGNATURES = {
     "pwclo_three_interpolate": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "pwclo_three_interpolate_grad": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "pwclo_knn": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "pwclo_set_conv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _LP, _i, _vp, _vp],
+    "pwclo_pointwise_mlp": [ctypes.POINTER(_vp), ctypes.POINTER(_i), _i, _i, _LP, _i, _vp, _vp],
+    "pwclo_cost_volume_1": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _LP, _LP, _LP, _vp, _vp],
+    "pwclo_cost_volume_2": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _LP, _LP, _vp, _vp],
+    "pwclo_pose_head": [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "pwclo_gather_rows3": [_vp, _vp, _i, _i, _i, _vp, _vp],
+    "pwclo_transpose": [_vp, _i, _i, _i, _i, _vp, _vp],
 }
 
 

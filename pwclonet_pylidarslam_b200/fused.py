@@ -1,4 +1,310 @@
-"""placeholder, replaced below"""
+"""Fused inference engine for PWCLONet (eval mode): BatchNorm folded into the 1x1 convolutions,
+one sm_100a kernel per layer, neighbour search with the pose warp fused in, both frames of the
+siamese pyramid batched into one launch per level.  Everything is driven through the C ABI of
+libpwclo_b200.so (include/pwclo_b200.h); torch only owns device memory and the stream.
+
+Layer-by-layer correspondence with the reference (PW = slam/models/PWCLONet,
+P2 = .../pointnet2_ops):
+    set_conv          P2/pointnet2_modules.py:179-245      (FPS -> gather -> kNN -> grouped MLP -> max)
+    set_upconv        P2/pointnet2_modules.py:459-515
+    cost_volume       PW/costvolume.py:63-190
+    flow_predictor    PW/flowpredictor.py:53-84
+    pose_head         PW/pose_calculator.py:47-87 + PW/pose_warp_refinement.py:120-148
+    forward           PW/pwclo_net.py:109-207
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _ext, _lib
+
+BN_EPS = 1e-5
+
+
+LayerT = _lib.LayerT
+_vp, _i = ctypes.c_void_p, ctypes.c_int
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side weight preparation
+# ------------------------------------------------------------------------------------------------
+def fold_conv_bn(sd, prefix):
+    """[Conv2d 1x1 (no bias) -> BatchNorm2d(eval)] -> (W [cout,cin], b [cout]) in float64
+    (P2/pytorch_utils.py:114-167; BN eps = nn.BatchNorm2d default)."""
+    w = sd[prefix + ".conv.weight"].double().reshape(sd[prefix + ".conv.weight"].shape[0], -1)
+    g, beta = sd[prefix + ".bn.bn.weight"].double(), sd[prefix + ".bn.bn.bias"].double()
+    mu, var = sd[prefix + ".bn.bn.running_mean"].double(), sd[prefix + ".bn.bn.running_var"].double()
+    s = g / torch.sqrt(var + BN_EPS)
+    return w * s[:, None], beta - mu * s
+
+
+def pack_layer(W, b, k_order=None, k4=None):
+    """W [cout,cin] -> the C-ABI layout [cout/CB][k4][CB] (CB = min(cout,64)), see include/pwclo_b200.h.
+    k_order: list of source columns (or -1 for a zero row) giving the kernel's internal input order."""
+    W = W.detach().double().cpu().numpy() if torch.is_tensor(W) else np.asarray(W, np.float64)
+    b = b.detach().double().cpu().numpy() if torch.is_tensor(b) else np.asarray(b, np.float64)
+    cout, cin = W.shape
+    if k_order is None:
+        k_order = list(range(cin))
+    kk = len(k_order)
+    k4 = (kk + 3) & ~3 if k4 is None else k4
+    assert k4 >= kk and k4 % 4 == 0
+    Wt = np.zeros((k4, cout), np.float64)
+    for dst, src in enumerate(k_order):
+        if src >= 0:
+            Wt[dst] = W[:, src]
+    cb = min(cout, 64)
+    assert cout % cb == 0
+    blocked = Wt.reshape(k4, cout // cb, cb).transpose(1, 0, 2)
+    return np.ascontiguousarray(blocked, np.float32).reshape(-1), b.astype(np.float32), cin, cout
+
+
+class WeightArena:
+    """All folded weights in ONE device buffer (3.1 MB), every tensor 256-byte aligned."""
+
+    def __init__(self):
+        self.chunks, self.size, self.pending = [], 0, []
+
+    def add(self, arr):
+        off = self.size
+        self.chunks.append((off, np.ascontiguousarray(arr, np.float32).reshape(-1)))
+        self.size = (off + arr.size * 4 + 255) & ~255
+        return off
+
+    def add_layer(self, packed):
+        w, b, cin, cout = packed
+        rec = {"w_off": self.add(w), "b_off": self.add(b), "cin": cin, "cout": cout}
+        self.pending.append(rec)
+        return rec
+
+    def finalize(self, device):
+        host = np.zeros(self.size // 4, np.float32)
+        for off, a in self.chunks:
+            host[off // 4: off // 4 + a.size] = a
+        self.buf = torch.from_numpy(host).to(device)
+        self.base = self.buf.data_ptr()
+        return self
+
+    def ptr(self, off):
+        return self.base + off
+
+    def layers(self, recs):
+        arr = (LayerT * len(recs))()
+        for i, r in enumerate(recs):
+            arr[i].w, arr[i].b, arr[i].cin, arr[i].cout = self.ptr(r["w_off"]), self.ptr(r["b_off"]), r["cin"], r["cout"]
+        return arr
+
+
+def _n_layers(sd, prefix):
+    n = 0
+    while f"{prefix}.layer{n}.conv.weight" in sd:
+        n += 1
+    return n
+
+
 class FusedPWCLONet:
     def __init__(self, net):
-        raise NotImplementedError
+        sd = {k: v.detach() for k, v in net.state_dict().items()}
+        dev = next(net.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.PwcloError("the fused PWCLO-Net engine needs the parameters on a CUDA device (no CPU fallback)")
+        self.device = dev
+        A = WeightArena()
+        self.A = A
+        self.recs = {}
+
+        def mlp(prefix, first_order=None, first_k4=None):
+            recs = []
+            for i in range(_n_layers(sd, prefix)):
+                W, b = fold_conv_bn(sd, f"{prefix}.layer{i}")
+                recs.append(A.add_layer(pack_layer(W, b, first_order if i == 0 else None, first_k4 if i == 0 else None)))
+            self.recs[prefix] = recs
+
+        def sa_order(cin):  # reference (xyz_diff(3), feat(C)) -> internal (feat(C), xyz_diff(3))
+            return list(range(3, cin)) + [0, 1, 2]
+
+        for name in ("psa_1", "psa_2", "psa_3", "psa_4", "flow_feature_encoding"):
+            cin = sd[f"{name}.mlp_module.layer0.conv.weight"].shape[1]
+            mlp(f"{name}.mlp_module", sa_order(cin))
+
+        def cost_volume(prefix):
+            cin = sd[f"{prefix}.mlp_convs.layer0.conv.weight"].shape[1]
+            order = list(range(10)) + [-1, -1] + list(range(10, cin))     # (geo(10), 0, 0, f1, f2)
+            mlp(f"{prefix}.mlp_convs", order)
+            mlp(f"{prefix}.mlp_conv_xyz_1")
+            mlp(f"{prefix}.mlp_conv_xyz_2")
+            mlp(f"{prefix}.mlp2_convs")
+            mlp(f"{prefix}.mlp3_convs")
+
+        def pose_calc(prefix):
+            r = {}
+            for nm in ("conv1d_q_t", "conv1d_q", "conv1d_t"):
+                w = sd[f"{prefix}.{nm}.conv.weight"].float().reshape(sd[f"{prefix}.{nm}.conv.weight"].shape[0], -1)
+                r[nm + ".w"] = A.add(w.cpu().numpy())
+                r[nm + ".b"] = A.add(sd[f"{prefix}.{nm}.conv.bias"].float().cpu().numpy())
+            self.recs[prefix] = r
+
+        cost_volume("cost_volume")
+        mlp("l4_flow_predictor.mlp_convs")
+        pose_calc("pose_calculator_4")
+        for l in (3, 2, 1):
+            p = f"pose_warp_refinement_{l}"
+            for up in ("setupconv_features", "setupconv_mask"):
+                mlp(f"{p}.{up}.mlp")          # reference order (features, xyz_diff) == internal order
+                mlp(f"{p}.{up}.post_mlp")
+            cost_volume(f"{p}.cost_volume")
+            mlp(f"{p}.flow_predictor_features.mlp_convs")
+            if l != 1:
+                mlp(f"{p}.flow_predictor_mask.mlp_convs")
+            pose_calc(f"{p}.pose_calculator")
+        A.finalize(dev)
+        self.L = {k: A.layers(v) for k, v in self.recs.items() if isinstance(v, list)}
+        self.lib = _lib.lib()
+        self.launches = 0
+        self.timeline = None     # when a list: (kernel name, start event, end event) per launch
+
+    # ------------------------------------------------------------------ thin launch helpers
+    def _call(self, name, *args):
+        if self.timeline is not None:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+        rc = getattr(self.lib, name)(*args, _lib.stream_ptr())
+        _lib.check(rc, name)
+        self.launches += 1
+        if self.timeline is not None:
+            e.record()
+            self.timeline.append((name, s, e))
+
+    def _new(self, *shape, dtype=torch.float32):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def fps(self, xyz, m):
+        B, N, _ = xyz.shape
+        idx = self._new(B, m, dtype=torch.int32)
+        self._call("pwclo_furthest_point_sampling", _p(xyz), B, N, m, 1, _p(idx))
+        return idx
+
+    def gather3(self, xyz, idx):
+        B, N, _ = xyz.shape
+        out = self._new(B, idx.shape[1], 3)
+        self._call("pwclo_gather_rows3", _p(xyz), _p(idx), B, N, idx.shape[1], _p(out))
+        return out
+
+    def knn(self, xyz, queries, k, warp_qt=None):
+        B, N, _ = xyz.shape
+        S = queries.shape[1]
+        idx = self._new(B, S, k, dtype=torch.int32)
+        warped = self._new(B, S, 3) if warp_qt is not None else None
+        self._call("pwclo_knn", _p(xyz), _p(queries), B, N, S, k, _ext.KNN_SUM_ORDER, _p(warp_qt), _p(warped), _p(idx),
+                   None)
+        return (idx, warped) if warp_qt is not None else idx
+
+    def set_conv(self, key, xyz, feats, new_xyz, idx):
+        B, N, _ = xyz.shape
+        S, K = idx.shape[1], idx.shape[2]
+        layers = self.L[key]
+        out = self._new(B, S, layers[len(layers) - 1].cout)
+        C = feats.shape[2] if feats is not None else 3
+        self._call("pwclo_set_conv", _p(xyz), _p(feats), _p(new_xyz), _p(idx), B, N, S, K, C, layers, len(layers), _p(out))
+        return out
+
+    def pointwise(self, key, srcs):
+        rows = srcs[0].shape[0] * srcs[0].shape[1]
+        layers = self.L[key]
+        out = self._new(srcs[0].shape[0], srcs[0].shape[1], layers[len(layers) - 1].cout)
+        ptrs = (_vp * len(srcs))(*[s.data_ptr() for s in srcs])
+        chans = (_i * len(srcs))(*[s.shape[2] for s in srcs])
+        self._call("pwclo_pointwise_mlp", ptrs, chans, len(srcs), rows, layers, len(layers), _p(out))
+        return out
+
+    def cost_volume(self, prefix, wxyz, f1, xyz2, f2, idx_q, idx_self):
+        B, S, _ = wxyz.shape
+        N, C = xyz2.shape[1], f1.shape[2]
+        e1 = self._new(B, S, 64)
+        self._call("pwclo_cost_volume_1", _p(wxyz), _p(f1), _p(xyz2), _p(f2), _p(idx_q), B, S, N, idx_q.shape[2], C,
+                   self.L[prefix + ".mlp_convs"], self.L[prefix + ".mlp_conv_xyz_1"], self.L[prefix + ".mlp2_convs"], _p(e1))
+        out = self._new(B, S, 64)
+        self._call("pwclo_cost_volume_2", _p(wxyz), _p(f1), _p(e1), _p(idx_self), B, S, idx_self.shape[2], C,
+                   self.L[prefix + ".mlp_conv_xyz_2"], self.L[prefix + ".mlp3_convs"], _p(out))
+        return out, e1
+
+    def pose_head(self, prefix, emb, mask, coarse_qt, pose_params, level):
+        B, S, _ = emb.shape
+        r = self.recs[prefix]
+        qt = self._new(B, 7)
+        P = self.A.ptr
+        self._call("pwclo_pose_head", _p(emb), _p(mask), B, S, P(r["conv1d_q_t.w"]), P(r["conv1d_q_t.b"]),
+                   P(r["conv1d_q.w"]), P(r["conv1d_q.b"]), P(r["conv1d_t.w"]), P(r["conv1d_t.b"]), _p(coarse_qt), _p(qt),
+                   _p(pose_params), level)
+        return qt
+
+    def to_point_major(self, x):
+        """[B,C,N] -> [B,N,C]"""
+        B, C, N = x.shape
+        out = self._new(B, N, C)
+        self._call("pwclo_transpose", _p(x.contiguous()), B, C, N, 1, _p(out))
+        return out
+
+    # ------------------------------------------------------------------ the network
+    LEVELS = ((2048, 32), (1024, 32), (256, 16), (64, 16))
+
+    def forward(self, xyz_f1, xyz_f2, trace=None):
+        """xyz_f1, xyz_f2: [B,3,N] fp32 CUDA -> (pose_params [B,4,7], embedding_mask_1 [B,64,2048] view,
+        new_xyz_f1_1 [B,2048,3])"""
+        B = xyz_f1.shape[0]
+        with torch.cuda.device(self.device):
+            # siamese pyramid: both frames share the weights -> one batch of 2B clouds per level
+            xyz = self.to_point_major(torch.cat((xyz_f1, xyz_f2), dim=0).float())
+            xs, fs, lvl_idx = [xyz], [None], []
+            for l, (npoint, k) in enumerate(self.LEVELS):
+                fidx = self.fps(xs[-1], npoint)
+                new_xyz = self.gather3(xs[-1], fidx)
+                idx = self.knn(xs[-1], new_xyz, k)
+                feats = self.set_conv(f"psa_{l + 1}.mlp_module", xs[-1], fs[-1], new_xyz, idx)
+                lvl_idx.append((fidx, idx))
+                xs.append(new_xyz)
+                fs.append(feats)
+            X1 = [None] + [x[:B] for x in xs[1:]]
+            X2 = [None] + [x[B:] for x in xs[1:]]
+            F1 = [None] + [f[:B] for f in fs[1:]]
+            F2 = [None] + [f[B:] for f in fs[1:]]
+            pose = self._new(B, 4, 7)
+
+            # coarse cost volume at level 3 + flow feature encoding (PW/pwclo_net.py:162-167)
+            idx_q = self.knn(X2[3], X1[3], 32)
+            idx_s = self.knn(X1[3], X1[3], 4)
+            emb, _ = self.cost_volume("cost_volume", X1[3], F1[3], X2[3], F2[3], idx_q, idx_s)
+            # flow_feature_encoding re-runs FPS + kNN on xyz1 of level 3: identical to psa_4's (frame 1)
+            emb4 = self.set_conv("flow_feature_encoding.mlp_module", X1[3], emb, X1[4], lvl_idx[3][1][:B])
+            mask4 = self.pointwise("l4_flow_predictor.mlp_convs", [F1[4], emb4])
+            qt = self.pose_head("pose_calculator_4", emb4, mask4, None, pose, 3)
+            if trace is not None:
+                trace.update({"cv3.out": emb, "l4.emb": emb4, "l4.mask": mask4, "l4.qt": qt})
+                for l in range(1, 5):
+                    trace[f"f1.psa{l}.feats"], trace[f"f2.psa{l}.feats"] = F1[l], F2[l]
+                    trace[f"psa{l}.fps_idx"], trace[f"psa{l}.knn_idx"] = lvl_idx[l - 1]
+
+            emb_prev, mask_prev = emb4, mask4
+            for l in (3, 2, 1):
+                p = f"pose_warp_refinement_{l}"
+                up_idx = self.knn(X1[l + 1], X1[l], 8)
+                m_f = self.set_conv(f"{p}.setupconv_features.mlp", X1[l + 1], emb_prev, X1[l], up_idx)
+                cf = self.pointwise(f"{p}.setupconv_features.post_mlp", [m_f, F1[l]])
+                m_m = self.set_conv(f"{p}.setupconv_mask.mlp", X1[l + 1], mask_prev, X1[l], up_idx)
+                cm = self.pointwise(f"{p}.setupconv_mask.post_mlp", [m_m, F1[l]])
+                idx_q, warped = self.knn(X2[l], X1[l], 6, warp_qt=qt)           # pose warp fused into the search
+                idx_s = self.knn(warped, warped, 4)
+                res, _ = self.cost_volume(f"{p}.cost_volume", warped, F1[l], X2[l], F2[l], idx_q, idx_s)
+                ef = self.pointwise(f"{p}.flow_predictor_features.mlp_convs", [F1[l], res, cf])
+                em = cm if l == 1 else self.pointwise(f"{p}.flow_predictor_mask.mlp_convs", [cm, ef, F1[l]])
+                qt = self.pose_head(f"{p}.pose_calculator", ef, em, qt, pose, l - 1)
+                if trace is not None:
+                    trace.update({f"pwr{l}.up_f": cf, f"pwr{l}.up_m": cm, f"pwr{l}.warped": warped, f"pwr{l}.cv": res,
+                                  f"pwr{l}.emb": ef, f"pwr{l}.mask": em, f"pwr{l}.qt": qt, f"pwr{l}.idx_q": idx_q})
+                emb_prev, mask_prev = ef, em
+        return pose, mask_prev.permute(0, 2, 1), X1[1]

@@ -1,0 +1,89 @@
+"""Per-layer parity of the fused inference engine against the oracle port,
+on identical seeded inputs and weights.  Both sides use the same kNN summation order so that the
+neighbour sets are identical and feature errors are pure arithmetic (tolerance: 1e-4 relative)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import _common as C
+
+pytestmark = pytest.mark.gpu
+
+
+def _cm(t):
+    """point-major [B,S,C] device tensor -> channel-major numpy [B,C,S] (the reference layout)"""
+    return t.permute(0, 2, 1).contiguous().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def run(cuda):
+    from oracle.pwclo_port import Port
+    from pwclonet_pylidarslam_b200 import _ext
+    from pwclonet_pylidarslam_b200.pwclonet import PWCLONet
+    g, x1, x2, wseed = C.load_golden("forward_b2_n8192_w1")
+    net = PWCLONet({"device": "cuda:0"})
+    w = C.weights_for({k: tuple(v.shape) for k, v in net.state_dict().items()}, wseed, g)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    net = net.to(cuda).eval()
+    old = _ext.KNN_SUM_ORDER
+    _ext.KNN_SUM_ORDER = 0
+    try:
+        trace = {}
+        with torch.no_grad():
+            pose, mask1, xyz1 = net.fused_engine().forward(torch.from_numpy(x1).to(cuda), torch.from_numpy(x2).to(cuda), trace)
+        torch.cuda.synchronize()
+    finally:
+        _ext.KNN_SUM_ORDER = old
+    port = Port(w, sum_order=0)
+    with torch.no_grad():
+        want, _ = port.forward(x1, x2)
+    return dict(pose=pose.cpu().numpy(), trace=trace, port=port, want=want.numpy(), B=x1.shape[0], g=g)
+
+
+def test_pyramid_indices_bit_exact(run):
+    t, port, B = run["trace"], run["port"], run["B"]
+    for l in range(1, 5):
+        fidx = t[f"psa{l}.fps_idx"].cpu().numpy()
+        kidx = t[f"psa{l}.knn_idx"].cpu().numpy()
+        for fr in (1, 2):
+            sl = slice(0, B) if fr == 1 else slice(B, 2 * B)
+            np.testing.assert_array_equal(fidx[sl], port.trace[f"f{fr}.psa{l}.fps_idx"].numpy())
+            np.testing.assert_array_equal(kidx[sl], port.trace[f"f{fr}.psa{l}.knn_idx"].numpy())
+
+
+@pytest.mark.parametrize("l", [1, 2, 3, 4])
+def test_set_conv_features(run, l):
+    for fr in (1, 2):
+        got = _cm(run["trace"][f"f{fr}.psa{l}.feats"])
+        want = run["port"].trace[f"f{fr}.psa{l}.feats"].numpy()
+        assert C.rel_err(got, want) <= C.TOL_FEATURE_REL, (l, fr, C.rel_err(got, want))
+
+
+def test_cost_volume_and_level4(run):
+    t, pt = run["trace"], run["port"].trace
+    assert C.rel_err(_cm(t["cv3.out"]), pt["cv3.out"].numpy()) <= C.TOL_FEATURE_REL
+    assert C.rel_err(_cm(t["l4.emb"]), pt["l4.emb"].numpy()) <= C.TOL_FEATURE_REL
+    assert C.rel_err(_cm(t["l4.mask"]), pt["l4.mask"].numpy()) <= C.TOL_FEATURE_REL
+    qt = t["l4.qt"].cpu().numpy()
+    np.testing.assert_allclose(qt[:, :4], pt["l4.q"].numpy(), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(qt[:, 4:], pt["l4.t"].numpy(), rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("l", [3, 2, 1])
+def test_pose_warp_refinement(run, l):
+    t, pt = run["trace"], run["port"].trace
+    np.testing.assert_allclose(_cm(t[f"pwr{l}.warped"]), pt[f"pwr{l}.warped"].numpy(), rtol=0, atol=2e-5)
+    np.testing.assert_array_equal(t[f"pwr{l}.idx_q"].cpu().numpy(), pt[f"pwr{l}.cv.idx_q"].numpy())
+    for key, pkey in (("up_f", "up_f.out"), ("up_m", "up_m.out"), ("cv", "cv.out"), ("emb", "emb"), ("mask", "mask")):
+        e = C.rel_err(_cm(t[f"pwr{l}.{key}"]), pt[f"pwr{l}.{pkey}"].numpy())
+        assert e <= C.TOL_FEATURE_REL, (l, key, e)
+    qt = t[f"pwr{l}.qt"].cpu().numpy()
+    np.testing.assert_allclose(qt[:, :4], pt[f"pwr{l}.q"].numpy(), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(qt[:, 4:], pt[f"pwr{l}.t"].numpy(), rtol=0, atol=1e-4)
+
+
+def test_final_pose(run):
+    te, re_ = C.pose_errors(run["pose"], run["want"])
+    assert te <= C.TOL_TRANSLATION_M and re_ <= C.TOL_ROTATION_RAD, (te, re_)
+    te, re_ = C.pose_errors(run["pose"], run["g"]["pose"])          # and against the unmodified reference's output
+    assert te <= C.TOL_TRANSLATION_M and re_ <= C.TOL_ROTATION_RAD, (te, re_)
