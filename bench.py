@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- PWCLO-Net frame-pairs/s (8192 points) on N B200, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one inference forward of the hot path (PWCLONet.forward, reference
+slam/models/PWCLONet/pwclo_net.py:109-207) over one batch of synthetic KITTI-64-beam-shaped frame
+pairs: BASELINE.json config "full 4-level hierarchical pose warp-refinement forward, batch 64 frame
+pairs", 64 pairs PER GPU (weak scaling: frame pairs are independent units, no data-path collective).
+
+  value      frame pairs/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public module API with inputs in pinned HOST memory: H2D copy
+             of the two clouds and D2H read of pose_params inside the timed region
+  roofline   the dominant kernel of the step, timed live with CUDA events on the launching stream
+  cpu_baseline  the oracle port of the reference forward (oracle/pwclo_port.py, validated bit-exact
+             against the unmodified reference) on this box's host cores, bounded sample
+  --impl reference  times that same CPU implementation as its own arm (rank 0 only)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "PWCLO-Net frame-pairs/s (8192 pts)"
+UNIT = "frame-pairs/s"
+N_POINTS = 8192
+FLOP_PER_PAIR = 6.04e9   # 3.018 G MACs of shared-MLP work per frame pair
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs-per-gpu", type=int, default=64)
+    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs generated per rank")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured"
+    except Exception:
+        return 6650.0, 1590.0, "fallback"
+
+
+def _gen_pair(seed):
+    from pwclonet_pylidarslam_b200 import synthetic as syn
+    p = syn.make_pair(seed, N_POINTS)
+    return p["pc1"], p["pc2"]
+
+
+def make_inputs(rank, pairs, distinct):
+    """`pairs` frame pairs [pairs,3,N] x2: `distinct` ray-cast scenes, replicated with a per-copy yaw
+    (a rigid motion applied to both frames keeps the pair's relative pose and the cloud statistics)."""
+    from concurrent.futures import ProcessPoolExecutor
+    from pwclonet_pylidarslam_b200 import synthetic as syn
+    distinct = min(distinct, pairs)
+    seeds = [syn.SEED_BASE + 1000 * rank + i for i in range(distinct)]
+    workers = max(1, min(distinct, (os.cpu_count() or 2) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
+    if workers > 1:
+        with ProcessPoolExecutor(workers) as ex:
+            got = list(ex.map(_gen_pair, seeds))
+    else:
+        got = [_gen_pair(s) for s in seeds]
+    rng = np.random.default_rng(rank)
+    x1, x2 = [], []
+    for i in range(pairs):
+        a, b = got[i % distinct]
+        if i >= distinct:
+            yaw = rng.uniform(0, 2 * np.pi)
+            c, s = np.cos(yaw), np.sin(yaw)
+            R = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], np.float32)
+            a, b = a @ R.T, b @ R.T
+        x1.append(a.T)
+        x2.append(b.T)
+    return np.ascontiguousarray(np.stack(x1), np.float32), np.ascontiguousarray(np.stack(x2), np.float32)
+
+
+def make_weights():
+    from pwclonet_pylidarslam_b200 import synthetic as syn
+    from pwclonet_pylidarslam_b200.pwclonet import PWCLONet
+    shapes = {k: tuple(v.shape) for k, v in PWCLONet({"device": "cpu"}).state_dict().items()}
+    return syn.make_state_dict(shapes, seed=1)
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference(weights, steps, warmup, pairs_per_step=1):
+    """The reference forward on the host cores: oracle port with the reference's own (materialising,
+    torch.topk) kNN formulation and all host threads.  Returns (pairs/s, ms/step, description)."""
+    from oracle.pwclo_port import Port
+    from pwclonet_pylidarslam_b200 import synthetic as syn
+    torch.set_num_threads(os.cpu_count() or 1)
+    port = Port(weights, knn_impl="torch")
+    x1, x2, _ = syn.make_batch(0, pairs_per_step, N_POINTS)
+    with torch.no_grad():
+        for _ in range(warmup):
+            port.forward(x1, x2)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            port.forward(x1, x2)
+        dt = time.perf_counter() - t0
+    return pairs_per_step * steps / dt, dt / steps * 1e3, f"{steps} forwards of {pairs_per_step} pair(s), N={N_POINTS}, after {warmup} warm-up"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    w = make_weights()
+    steps = max(1, min(args.steps, 8))
+    v, ms, sample = cpu_reference(w, steps, max(1, min(args.warmup, 2)))
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "PWCLO-Net inference forward, 8192-point synthetic KITTI-64-beam frame pairs, "
+                                   "reference CPU path (oracle port of the reference forward; the reference's CUDA "
+                                   "extension has no CPU path), 1 pair per step"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1 and args.impl == "ours":
+        # convenience: re-launch under torchrun
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
+                                   "29533", os.path.abspath(__file__)] + sys.argv[1:])
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    P = args.pairs_per_gpu
+    h1, h2 = make_inputs(rank, P, args.distinct)      # host-side ray casting (forks workers) before CUDA comes up
+    import torch.distributed as dist
+    from pwclonet_pylidarslam_b200 import _lib
+    from pwclonet_pylidarslam_b200.pwclonet import PWCLONet
+    _lib.lib()   # fail loudly right away if the CUDA library is missing
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    weights = make_weights()
+    net = PWCLONet({"device": str(dev)})
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    net = net.to(dev).eval()
+    pin1, pin2 = torch.from_numpy(h1).pin_memory(), torch.from_numpy(h2).pin_memory()
+    d1, d2 = pin1.to(dev), pin2.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    eng = net.fused_engine()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        with torch.no_grad():
+            return net(d1, None, d2, None)[0]
+
+    def step_e2e():
+        with torch.no_grad():
+            a = pin1.to(dev, non_blocking=True)
+            b = pin2.to(dev, non_blocking=True)
+            return net(a, None, b, None)[0].cpu()
+
+    def timed(fn, steps):
+        evs = []
+        for _ in range(steps):
+            flush.zero_()                       # L2 flush between timed iterations (outside the timed events)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn()
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs), out
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = eng.launches
+    ms_total, pose = timed(step_resident, args.steps)
+    launches = eng.launches - launches0
+    barrier()
+    sampler.stop_flag = True
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    barrier()
+
+    # per-kernel timeline (CUDA events around every launch of one extra step) -> dominant kernel
+    eng.timeline = []
+    step_resident()
+    torch.cuda.synchronize()
+    per_kernel = {}
+    for name, s, e in eng.timeline:
+        per_kernel.setdefault(name, []).append(s.elapsed_time(e))
+    eng.timeline = None
+    step_ms = ms_total / args.steps
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    value = world * P * args.steps / (ms_total * 1e-3)
+    e2e = world * P * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        hbm_peak, tf_peak, peak_kind = peaks()
+        shares = sorted(((sum(v), k, len(v)) for k, v in per_kernel.items()), reverse=True)
+        tot = sum(s for s, _, _ in shares)
+        top_ms, top_name, top_n = shares[0]
+        # the grouped-MLP kernels are fp32 FFMA work: report them against the tensor roofline the
+        # north star sets for the 1x1 contractions; the neighbour search against its compulsory bytes.
+        mlp_kernels = {"pwclo_set_conv", "pwclo_pointwise_mlp", "pwclo_cost_volume_1", "pwclo_cost_volume_2"}
+        if top_name in mlp_kernels:
+            mlp_ms = sum(s for s, k, _ in shares if k in mlp_kernels)
+            ach = FLOP_PER_PAIR * P / (mlp_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "fused grouped-MLP layer kernels (fp32 FFMA)", "achieved": ach,
+                    "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None, "peak_kind": peak_kind,
+                    "ms_per_step": mlp_ms}
+        else:
+            # kNN / FPS: compulsory bytes of SURVEY 8d per frame pair (level-1 dominated)
+            alg = {"pwclo_knn": 4 * 2 * (3 * 2048 + 3 * 8192 + 2048 * 32), "pwclo_furthest_point_sampling": 4 * 2 * (3 * 8192 + 2048)}
+            by = alg.get(top_name, 0) * P
+            ach = by / (top_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": top_name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_kind": peak_kind, "ms_per_step": top_ms}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"PWCLO-Net full 4-level inference forward, {P} frame pairs per GPU x {N_POINTS} points "
+                                       "(BASELINE config: batch 64 frame pairs), synthetic KITTI-64-beam clouds, random-init "
+                                       "weights with non-trivial BN statistics",
+                           "pairs_per_gpu": P, "points": N_POINTS, "l2": "flushed between timed steps (256 MB write)",
+                           "parallelism": f"frame-pair sharding x{world}, no collective"},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pin1.numel() * 4 * 2),
+                        "d2h_bytes_per_step": int(pose.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches),
+                "clocks": sampler.summary(),
+                "roofline": roof,
+                "kernel_shares": [{"kernel": k, "ms": round(s, 4), "launches": n, "share": round(s / tot, 4)} for s, k, n in shares],
+                "step_ms_rank0": step_ms}
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, sample = cpu_reference(weights, 5, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": sample, "ms_per_pair": ms}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
