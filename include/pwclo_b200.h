@@ -20,6 +20,7 @@
 #ifndef PWCLO_B200_H
 #define PWCLO_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -88,6 +89,16 @@ int pwclo_three_interpolate_grad(const float *grad_out, const int32_t *idx, cons
  * (if warped_out != NULL) the transformed queries are written to warped_out[B,S,3]. */
 int pwclo_knn(const float *xyz, const float *new_xyz, int B, int N, int S, int K, int sum_order,
               const float *warp_qt, float *warped_out, int32_t *idx, float *dist, void *stream);
+
+/* Same contract and bit-identical result as pwclo_knn, but exact search with sorted-slab pruning:
+ * the reference points of every cloud are first sorted along their widest axis into `workspace`
+ * (pwclo_knn_workspace_bytes(B,N) bytes, 16-byte aligned, caller-owned scratch), then each query scans
+ * outwards from its own position only as far as its current K-th distance allows.  Falls back to
+ * the brute-force kernel when N > 8192 or the workspace is missing / too small. */
+size_t pwclo_knn_workspace_bytes(int B, int N);
+int pwclo_knn_sorted(const float *xyz, const float *new_xyz, int B, int N, int S, int K,
+                     int sum_order, const float *warp_qt, float *warped_out, int32_t *idx,
+                     float *dist, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- B2: fused inference layers (BatchNorm folded by the host side) ------------------------------
  * Feature tensors are POINT-MAJOR [B,N,C] fp32 (the reference keeps [B,C,N]; pwclo_transpose

@@ -143,6 +143,8 @@ def three_interpolate_grad(grad_out, idx, weight, m):
 
 
 # ---- not part of the reference extension: the kNN the reference does in PyTorch -----------------
+KNN_SORTED = True          # exact sorted-slab search (pwclo_knn_sorted) instead of brute force
+KNN_SORTED_MIN_N = 64      # below this many reference points brute force is used
 KNN_SUM_ORDER = 1  # PWCLO_KNN_SUM_XZ_Y: torch's CUDA reduction order (see DESIGN.md "kNN formulation")
 
 
@@ -160,10 +162,17 @@ def knn(xyz, new_xyz, k, sum_order=None, warp_qt=None, return_warped=False, retu
             warped = torch.empty_like(new_xyz)
     so = KNN_SUM_ORDER if sum_order is None else int(sum_order)
     with torch.cuda.device(xyz.device):
-        _lib.check(_lib.lib().pwclo_knn(_p(xyz), _p(new_xyz), B, N, S, int(k), so,
-                                        _p(warp_qt) if warp_qt is not None else None,
-                                        _p(warped) if warped is not None else None,
-                                        _p(idx), _p(dist) if dist is not None else None, _lib.stream_ptr()), "knn")
+        L = _lib.lib()
+        wq = _p(warp_qt) if warp_qt is not None else None
+        wo = _p(warped) if warped is not None else None
+        dp = _p(dist) if dist is not None else None
+        ws_bytes = L.pwclo_knn_workspace_bytes(B, N) if KNN_SORTED and N >= KNN_SORTED_MIN_N else 0
+        if ws_bytes:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device)
+            _lib.check(L.pwclo_knn_sorted(_p(xyz), _p(new_xyz), B, N, S, int(k), so, wq, wo, _p(idx), dp, _p(ws), ws_bytes,
+                                          _lib.stream_ptr()), "knn_sorted")
+        else:
+            _lib.check(L.pwclo_knn(_p(xyz), _p(new_xyz), B, N, S, int(k), so, wq, wo, _p(idx), dp, _lib.stream_ptr()), "knn")
     out = [idx]
     if return_dist:
         out.append(dist)

@@ -32,6 +32,7 @@ SIGNATURES = {
     "pwclo_three_interpolate": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "pwclo_three_interpolate_grad": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "pwclo_knn": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "pwclo_knn_sorted": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp],
     "pwclo_set_conv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _LP, _i, _vp, _vp],
     "pwclo_pointwise_mlp": [ctypes.POINTER(_vp), ctypes.POINTER(_i), _i, _i, _LP, _i, _vp, _vp],
     "pwclo_cost_volume_1": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _LP, _LP, _LP, _vp, _vp],
@@ -58,6 +59,8 @@ def lib():
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = ctypes.c_int
+        L.pwclo_knn_workspace_bytes.argtypes = [_i, _i]
+        L.pwclo_knn_workspace_bytes.restype = ctypes.c_size_t
         L.pwclo_version.restype = ctypes.c_char_p
         L.pwclo_error_string.restype = ctypes.c_char_p
         L.pwclo_error_string.argtypes = [ctypes.c_int]

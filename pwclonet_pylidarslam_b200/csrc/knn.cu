@@ -242,3 +242,270 @@ PWCLO_API int pwclo_knn(const float* xyz, const float* new_xyz, int B, int N, in
     return launch_knn<2>(xyz, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist, st);
   return launch_knn<1>(xyz, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist, st);
 }
+
+// =================================================================================================
+// Sorted-slab exact kNN (the default path for N <= 8192 when the caller provides a workspace).
+//
+// Brute force evaluates S*N pairs; for LiDAR clouds the K-th neighbour is ~0.5 m away while the
+// cloud spans ~60 m, so almost all of that work is provably useless.  Two kernels:
+//   1. knn_presort_kernel: one CTA per cloud sorts the reference points along the axis of largest
+//      extent (64-bit (ordered coordinate, index) keys, bitonic sort in shared memory) and writes
+//      the sorted SoA (x, y, z, original index) + the axis id to the workspace.
+//   2. knn_slab_kernel: the sorted cloud is staged in shared memory by ONE TMA bulk copy; a warp
+//      binary-searches its query's position and scans 32-point chunks outwards on both sides,
+//      nearest side first, until the squared axis distance of the next unscanned point exceeds the
+//      conservative bound of the current K-th neighbour.  Distances, keys, queueing and merging are
+//      exactly those of the brute-force kernel, so the result is bit-identical: a skipped point has
+//      d2 >= dx2 > bound, hence sqrt(d2+1e-8) > K-th distance (strictly).
+// =================================================================================================
+namespace pwclo {
+
+constexpr int SORT_THREADS = 1024;
+constexpr int SLAB_WARPS = 16;
+
+__device__ __forceinline__ unsigned ordered_bits(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__host__ __device__ inline size_t knn_ws_stride(int N) { return (size_t)4 * ((N + 3) & ~3) + 4; }  // floats per cloud
+
+__global__ void __launch_bounds__(SORT_THREADS)
+knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, float* __restrict__ ws) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  u64* keys = reinterpret_cast<u64*>(sort_smem);
+  __shared__ float red[6][32];
+  __shared__ int axis_s;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  xyz += (size_t)b * N * 3;
+  float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+  for (int i = tid; i < N; i += SORT_THREADS)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float v = xyz[i * 3 + d];
+      mn[d] = fminf(mn[d], v);
+      mx[d] = fmaxf(mx[d], v);
+    }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    for (int off = 16; off; off >>= 1) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(PWCLO_FULL_MASK, mn[d], off));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(PWCLO_FULL_MASK, mx[d], off));
+    }
+    if (lane == 0) { red[d][warp] = mn[d]; red[3 + d][warp] = mx[d]; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float ext[3];
+    for (int d = 0; d < 3; ++d) {
+      float a = CUDART_INF_F, c = -CUDART_INF_F;
+      for (int w = 0; w < SORT_THREADS / 32; ++w) { a = fminf(a, red[d][w]); c = fmaxf(c, red[3 + d][w]); }
+      ext[d] = c - a;
+    }
+    axis_s = (ext[0] >= ext[1] && ext[0] >= ext[2]) ? 0 : (ext[2] >= ext[1] ? 2 : 1);
+  }
+  __syncthreads();
+  const int axis = axis_s;
+  for (int i = tid; i < NP; i += SORT_THREADS)
+    keys[i] = i < N ? (((u64)ordered_bits(xyz[i * 3 + axis]) << 32) | (unsigned)i) : ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= NP; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < NP / 2; t += SORT_THREADS) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j cleared
+        const int hi = lo | j;
+        const u64 a = keys[lo], c = keys[hi];
+        const bool up = (lo & k) == 0;
+        if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  const int N4 = (N + 3) & ~3;
+  float* w = ws + (size_t)b * knn_ws_stride(N);
+  for (int i = tid; i < N4; i += SORT_THREADS) {
+    float x = CUDART_INF_F, y = CUDART_INF_F, z = CUDART_INF_F;
+    int id = 0;
+    if (i < N) {
+      id = (int)(unsigned)keys[i];
+      x = xyz[id * 3 + 0]; y = xyz[id * 3 + 1]; z = xyz[id * 3 + 2];
+    }
+    w[i] = x; w[N4 + i] = y; w[2 * N4 + i] = z;
+    reinterpret_cast<int*>(w)[3 * N4 + i] = id;
+  }
+  if (tid == 0) reinterpret_cast<int*>(w)[4 * N4] = axis;
+}
+
+__device__ __forceinline__ void slab_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+
+template <int SUM_ORDER>
+__global__ void __launch_bounds__(SLAB_WARPS * 32)
+knn_slab_kernel(const float* __restrict__ ws, const float* __restrict__ new_xyz, int N, int S, int K, int q_per_cta,
+                const float* __restrict__ warp_qt, float* __restrict__ warped_out, int32_t* __restrict__ idx_out,
+                float* __restrict__ dist_out) {
+  extern __shared__ __align__(128) unsigned char slab_smem[];
+  const int N4 = (N + 3) & ~3;
+  float* sx = reinterpret_cast<float*>(slab_smem);
+  float* sy = sx + N4;
+  float* sz = sy + N4;
+  int* sid = reinterpret_cast<int*>(sz + N4);
+  int* hdr = sid + N4;                        // [0] = axis
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* cand_d = reinterpret_cast<float*>(hdr + 4) + (size_t)warp * KNN_BUF;
+  int* cand_i = reinterpret_cast<int*>(reinterpret_cast<float*>(hdr + 4) + (size_t)SLAB_WARPS * KNN_BUF) + (size_t)warp * KNN_BUF;
+  __shared__ __align__(8) uint64_t bar;
+
+  const int b = blockIdx.y;
+  const float* w = ws + (size_t)b * knn_ws_stride(N);
+  if (threadIdx.x == 0) {
+    const uint32_t baddr = (uint32_t)__cvta_generic_to_shared(&bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(baddr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)(knn_ws_stride(N) * sizeof(float));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(baddr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(sx)),
+                 "l"(w), "r"(bytes), "r"(baddr)
+                 : "memory");
+  }
+  __syncthreads();   // barrier initialised before anyone polls it
+  new_xyz += (size_t)b * S * 3;
+  PoseQT pose;
+  const bool do_warp = warp_qt != nullptr;
+  if (do_warp) pose = make_pose(warp_qt + (size_t)b * 7);
+  slab_mbar_wait(&bar, 0);
+  const int axis = hdr[0];
+  const float* sa = axis == 0 ? sx : (axis == 1 ? sy : sz);
+
+  const int flush_at = min(32, max(2 * K, 8));
+  const int q_end = min(S, (int)(blockIdx.x + 1) * q_per_cta);
+  for (int q = blockIdx.x * q_per_cta + warp; q < q_end; q += SLAB_WARPS) {
+    float qx = new_xyz[q * 3 + 0], qy = new_xyz[q * 3 + 1], qz = new_xyz[q * 3 + 2];
+    if (do_warp) {
+      warp_point(pose, qx, qy, qz, qx, qy, qz);
+      if (warped_out != nullptr && lane == 0) {
+        float* o = warped_out + ((size_t)b * S + q) * 3;
+        o[0] = qx; o[1] = qy; o[2] = qz;
+      }
+    }
+    const float qa = axis == 0 ? qx : (axis == 1 ? qy : qz);
+    // first sorted position with sa[pos] >= qa
+    int lo_b = 0, hi_b = N;
+    while (lo_b < hi_b) {
+      const int mid = (lo_b + hi_b) >> 1;
+      if (sa[mid] < qa) lo_b = mid + 1; else hi_b = mid;
+    }
+    int left = lo_b - 1, right = lo_b;   // nearest unscanned positions on each side
+    u64 list = KNN_INF_KEY;
+    float bound = CUDART_INF_F;
+    int cnt = 0;
+    while (left >= 0 || right < N) {
+      float el = CUDART_INF_F, er = CUDART_INF_F;   // squared axis distance of the nearest unscanned point
+      if (left >= 0) { const float d = __fsub_rn(qa, sa[left]); el = __fmul_rn(d, d); }
+      if (right < N) { const float d = __fsub_rn(qa, sa[right]); er = __fmul_rn(d, d); }
+      const bool go_left = el <= er;
+      const float e = go_left ? el : er;
+      if (!(e <= bound)) break;          // both sides exhausted or provably too far (also ends on inf/inf)
+      int pos;
+      if (go_left) { pos = left - lane; left -= 32; }
+      else { pos = right + lane; right += 32; }
+      const bool rv = pos >= 0 && pos < N;
+      const int pc = rv ? pos : 0;
+      const float dx = __fsub_rn(qx, sx[pc]), dy = __fsub_rn(qy, sy[pc]), dz = __fsub_rn(qz, sz[pc]);
+      const float xx = __fmul_rn(dx, dx), yy = __fmul_rn(dy, dy), zz = __fmul_rn(dz, dz);
+      const float d2 = SUM_ORDER == 0 ? __fadd_rn(__fadd_rn(xx, yy), zz) : __fadd_rn(__fadd_rn(xx, zz), yy);
+      const bool pass = rv && d2 <= bound;
+      const unsigned mask = __ballot_sync(PWCLO_FULL_MASK, pass);
+      if (mask) {
+        if (pass) {
+          const int slot = cnt + __popc(mask & ((1u << lane) - 1u));
+          cand_d[slot] = d2;
+          cand_i[slot] = sid[pc];
+        }
+        cnt += __popc(mask);
+        if (cnt >= flush_at) {   // small K: merge early so that the pruning bound tightens early
+          __syncwarp();
+          const u64 ck = lane < cnt ? knn_key(__fsqrt_rn(__fadd_rn(cand_d[lane], 1e-8f)), cand_i[lane]) : KNN_INF_KEY;
+          const int rest = max(cnt - 32, 0);
+          float md = 0.f; int mi = 0;
+          if (lane < rest) { md = cand_d[32 + lane]; mi = cand_i[32 + lane]; }
+          __syncwarp();
+          if (lane < rest) { cand_d[lane] = md; cand_i[lane] = mi; }
+          cnt = rest;
+          list = knn_merge32(list, ck, lane);
+          bound = knn_bound(__uint_as_float((unsigned)(shfl_u64(list, K - 1) >> 32)));
+        }
+      }
+    }
+    if (cnt > 0) {
+      __syncwarp();
+      const u64 ck = lane < cnt ? knn_key(__fsqrt_rn(__fadd_rn(cand_d[lane], 1e-8f)), cand_i[lane]) : KNN_INF_KEY;
+      list = knn_merge32(list, ck, lane);
+    }
+    __syncwarp();
+    if (lane < K) {
+      const size_t o = ((size_t)b * S + q) * K + lane;
+      idx_out[o] = (int)(unsigned)list;
+      if (dist_out) dist_out[o] = __uint_as_float((unsigned)(list >> 32));
+    }
+  }
+}
+
+}  // namespace pwclo
+
+PWCLO_API size_t pwclo_knn_workspace_bytes(int B, int N) {
+  if (B <= 0 || N <= 0 || N > KNN_MAX_TILE) return 0;
+  return (size_t)B * knn_ws_stride(N) * sizeof(float);
+}
+
+PWCLO_API int pwclo_knn_sorted(const float* xyz, const float* new_xyz, int B, int N, int S, int K, int sum_order,
+                               const float* warp_qt, float* warped_out, int32_t* idx, float* dist, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (!xyz || !new_xyz || !idx || B < 0 || N <= 0 || S < 0 || K <= 0) return PWCLO_EINVAL;
+  if (K > 32) return PWCLO_EUNSUPPORTED;
+  if (K > N) return PWCLO_EINVAL;
+  if (sum_order != PWCLO_KNN_SUM_XY_Z && sum_order != PWCLO_KNN_SUM_XZ_Y) return PWCLO_EINVAL;
+  if (B == 0 || S == 0) return PWCLO_OK;
+  if (B > 65535) return PWCLO_EUNSUPPORTED;
+  if (N > KNN_MAX_TILE || !workspace || workspace_bytes < pwclo_knn_workspace_bytes(B, N) || (uintptr_t)workspace % 16 != 0)
+    return pwclo_knn(xyz, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  int NP = 1;
+  while (NP < N) NP <<= 1;
+  {
+    const size_t smem = (size_t)NP * sizeof(u64);
+    if (smem > 32 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(knn_presort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    knn_presort_kernel<<<B, SORT_THREADS, smem, st>>>(xyz, N, NP, (float*)workspace);
+    int rc = launch_status();
+    if (rc) return rc;
+  }
+  const size_t smem = knn_ws_stride(N) * sizeof(float) + (size_t)SLAB_WARPS * KNN_BUF * 8 + 128;
+  // queries per CTA: amortise the shared-memory fill, keep >= ~3 CTAs per SM in flight overall
+  int q_per_cta = SLAB_WARPS;
+  while (q_per_cta * 2 <= S && (long long)B * ceil_div(S, q_per_cta * 2) >= 3LL * kNumSM) q_per_cta *= 2;
+  auto kern = sum_order == PWCLO_KNN_SUM_XY_Z ? knn_slab_kernel<0> : knn_slab_kernel<1>;
+  if (smem > 32 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  dim3 grid(ceil_div(S, q_per_cta), B);
+  kern<<<grid, SLAB_WARPS * 32, smem, st>>>((const float*)workspace, new_xyz, N, S, K, q_per_cta, warp_qt, warped_out, idx, dist);
+  return launch_status();
+}

@@ -119,6 +119,116 @@ __global__ void __launch_bounds__(LT) set_conv_kernel(const SAArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// narrow set conv (pyramid levels 1-3: widths <= 64).  One lane per (point, neighbour) row: the row's
+// inputs and all intermediate activations live in registers, weights are broadcast-read from shared
+// memory, and the max over the K neighbours is a log-step shuffle transpose-reduce.  No activation
+// ever touches shared memory; the GEMM-tile kernel above wastes most of its tile on these widths.
+// ------------------------------------------------------------------------------------------------
+template <int CIN4, int COUT>
+__device__ __forceinline__ void small_layer(const float (&x)[CIN4], float (&y)[COUT], const float* __restrict__ w,
+                                            const float* __restrict__ b) {
+#pragma unroll
+  for (int n = 0; n < COUT; n += 4) {
+    const float4 bv = *reinterpret_cast<const float4*>(b + n);
+    y[n] = bv.x; y[n + 1] = bv.y; y[n + 2] = bv.z; y[n + 3] = bv.w;
+  }
+#pragma unroll
+  for (int k = 0; k < CIN4; ++k) {
+#pragma unroll
+    for (int n = 0; n < COUT; n += 4) {
+      const float4 wv = *reinterpret_cast<const float4*>(w + k * COUT + n);
+      y[n] = fmaf(x[k], wv.x, y[n]);
+      y[n + 1] = fmaf(x[k], wv.y, y[n + 1]);
+      y[n + 2] = fmaf(x[k], wv.z, y[n + 2]);
+      y[n + 3] = fmaf(x[k], wv.w, y[n + 3]);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < COUT; ++n) y[n] = fmaxf(y[n], 0.f);
+}
+
+template <int K, int C, int C1, int C2, int C3>
+__global__ void __launch_bounds__(256) set_conv_small_kernel(const SAArgs a, int total_points) {
+  constexpr int CIN4 = (C + 3 + 3) & ~3;
+  constexpr int PPW = 32 / K;              // points per warp
+  __shared__ __align__(16) float w1[CIN4 * C1], w2[C1 * C2], w3[C2 * C3], b1[C1], b2[C2], b3[C3];
+  for (int i = threadIdx.x; i < CIN4 * C1; i += 256) w1[i] = a.l[0].w[i];
+  for (int i = threadIdx.x; i < C1 * C2; i += 256) w2[i] = a.l[1].w[i];
+  for (int i = threadIdx.x; i < C2 * C3; i += 256) w3[i] = a.l[2].w[i];
+  for (int i = threadIdx.x; i < C1; i += 256) b1[i] = a.l[0].b[i];
+  for (int i = threadIdx.x; i < C2; i += 256) b2[i] = a.l[1].b[i];
+  for (int i = threadIdx.x; i < C3; i += 256) b3[i] = a.l[2].b[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / K, k = lane % K;
+  const int warp_global = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * 8;
+#pragma unroll 1
+  for (int g0 = warp_global * PPW; g0 < total_points; g0 += nwarps * PPW) {
+    asm volatile("" ::: "memory");                    // keep the (loop-invariant) weights in shared memory, not registers
+    const int g = min(g0 + sub, total_points - 1);    // (cloud, point) flattened
+    const int b = g / a.S;
+    const int n = a.idx[(size_t)g * K + k];
+    const float* q = a.xyz + ((size_t)b * a.N + n) * 3;
+    const float* ctr = a.new_xyz + (size_t)g * 3;
+    float x[CIN4];
+    const float qx = q[0], qy = q[1], qz = q[2];
+    if (a.feats == nullptr) {
+      x[0] = qx; x[1] = qy; x[2] = qz;
+    } else {
+      const float4* f = reinterpret_cast<const float4*>(a.feats + ((size_t)b * a.N + n) * C);
+#pragma unroll
+      for (int c = 0; c < C / 4; ++c) {
+        const float4 v = __ldg(f + c);
+        x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+      }
+    }
+    x[C] = __fsub_rn(qx, ctr[0]); x[C + 1] = __fsub_rn(qy, ctr[1]); x[C + 2] = __fsub_rn(qz, ctr[2]);
+#pragma unroll
+    for (int c = C + 3; c < CIN4; ++c) x[c] = 0.f;
+    float h1[C1], h2[C2], v[C3];
+    small_layer<CIN4, C1>(x, h1, w1, b1);
+    small_layer<C1, C2>(h1, h2, w2, b2);
+    small_layer<C2, C3>(h2, v, w3, b3);
+    // max over the K lanes of a point: transpose-reduce, every step halves the live values per lane
+    int nlive = C3, chan = 0;
+#pragma unroll
+    for (int off = K / 2; off >= 1; off >>= 1) {
+      const bool upper = (lane & off) != 0;
+      if (nlive > 1) {
+        const int half = nlive / 2;
+#pragma unroll
+        for (int i = 0; i < C3 / 2; ++i) {
+          if (i < half) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = fmaxf(keep, __shfl_xor_sync(PWCLO_FULL_MASK, send, off));
+          }
+        }
+        chan += upper ? half : 0;
+        nlive = half;
+      } else {
+        v[0] = fmaxf(v[0], __shfl_xor_sync(PWCLO_FULL_MASK, v[0], off));
+      }
+    }
+    // lane now holds `nlive` consecutive channels starting at chan*? (see below)
+    if (g0 + sub < total_points) {
+      float* o = a.out + (size_t)g * C3;
+      if (nlive == 1) {
+        // when K >= C3 several lanes hold the same channel: let the lowest one write
+        const int dup = K / C3 > 1 ? K / C3 : 1;        // lanes per channel
+        if ((k % dup) == 0 || C3 >= K) o[chan] = v[0];
+      } else {
+#pragma unroll
+        for (int i = 0; i < C3; ++i)
+          if (i < nlive) o[chan + i] = v[i];
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // point-wise MLP on the concatenation of up to three point-major tensors (1 or 2 layers)
 // ------------------------------------------------------------------------------------------------
@@ -351,15 +461,16 @@ struct PoseArgs {
   int S;
 };
 
-__global__ void __launch_bounds__(256) pose_head_kernel(const PoseArgs a) {
-  __shared__ float pm[4][64], pz[4][64], ps[4][64];
+constexpr int POSE_PARTS = 16;   // 1024 threads: 16 slices of the point axis x 64 channels
+__global__ void __launch_bounds__(POSE_PARTS * 64) pose_head_kernel(const PoseArgs a) {
+  __shared__ float pm[POSE_PARTS][64], pz[POSE_PARTS][64], ps[POSE_PARTS][64];
   __shared__ float sv[64], big[256], qd[4], td[3];
   const int tid = threadIdx.x, b = blockIdx.x;
   const int c = tid & 63, part = tid >> 6;
   const float* E = a.emb + (size_t)b * a.S * 64;
   const float* M = a.mask + (size_t)b * a.S * 64;
   float m = -CUDART_INF_F, z = 0.f, s = 0.f;
-  for (int n = part; n < a.S; n += 4) {
+  for (int n = part; n < a.S; n += POSE_PARTS) {
     const float v = M[(size_t)n * 64 + c];
     const float f = E[(size_t)n * 64 + c];
     if (v > m) { const float sc = expf(m - v); z *= sc; s *= sc; m = v; }
@@ -370,9 +481,10 @@ __global__ void __launch_bounds__(256) pose_head_kernel(const PoseArgs a) {
   pm[part][c] = m; pz[part][c] = z; ps[part][c] = s;
   __syncthreads();
   if (tid < 64) {
-    float mm = fmaxf(fmaxf(pm[0][tid], pm[1][tid]), fmaxf(pm[2][tid], pm[3][tid]));
+    float mm = pm[0][tid];
+    for (int i = 1; i < POSE_PARTS; ++i) mm = fmaxf(mm, pm[i][tid]);
     float zz = 0.f, ss = 0.f;
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < POSE_PARTS; ++i) {
       const float sc = pz[i][tid] > 0.f ? expf(pm[i][tid] - mm) : 0.f;
       zz += pz[i][tid] * sc;
       ss += ps[i][tid] * sc;
@@ -380,7 +492,7 @@ __global__ void __launch_bounds__(256) pose_head_kernel(const PoseArgs a) {
     sv[tid] = ss / zz;
   }
   __syncthreads();
-  {
+  if (tid < 256) {
     float acc = a.bqt[tid];
     const float* w = a.wqt + (size_t)tid * 64;
     for (int k = 0; k < 64; ++k) acc = fmaf(w[k], sv[k], acc);
@@ -511,6 +623,21 @@ PWCLO_API int pwclo_set_conv(const float* xyz, const float* feats, const float* 
     return al128((size_t)R * a.ldA * 4) + al128((size_t)R * a.ldB * 4) + kRingBytes + al128(R * 4) + al128(3 * R * 4) + 128;
   };
   cudaStream_t st = (cudaStream_t)stream;
+  if (nlayers == 3 && !getenv("PWCLO_NO_SMALL_SA")) {   // register-resident kernel for the narrow pyramid levels
+    const int c1 = a.l[0].cout, c2 = a.l[1].cout, c3 = a.l[2].cout;
+    const int total = B * S;
+#define SMALL_CASE(KK, CC, A1, A2, A3)                                                                   \
+  if (K == KK && C == CC && c1 == A1 && c2 == A2 && c3 == A3) {                                          \
+    const int ppw = 32 / KK;                                                                             \
+    const int blocks = min(ceil_div(total, 8 * ppw), kNumSM * 8);                                        \
+    set_conv_small_kernel<KK, CC, A1, A2, A3><<<blocks, 256, 0, st>>>(a, total);                         \
+    return launch_status();                                                                              \
+  }
+    SMALL_CASE(32, 3, 8, 8, 16)
+    SMALL_CASE(32, 16, 16, 16, 32)
+    SMALL_CASE(16, 32, 32, 32, 64)
+#undef SMALL_CASE
+  }
   if (narrow || (smem_for(128) <= 100 * 1024 && K <= 128)) {
     dim3 grid(ceil_div(S, 128 / K), B);
     return launch_layer(set_conv_kernel<128>, a, grid, smem_for(128), st);
@@ -617,7 +744,7 @@ PWCLO_API int pwclo_pose_head(const float* emb, const float* mask, int B, int S,
   PoseArgs a;
   a.emb = emb; a.mask = mask; a.wqt = wqt; a.bqt = bqt; a.wq = wq; a.bq = bq; a.wt = wt; a.bt = bt;
   a.coarse = coarse_qt; a.qt_out = qt_out; a.pose_row = pose_params + level * 7; a.S = S;
-  pose_head_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(a);
+  pose_head_kernel<<<B, POSE_PARTS * 64, 0, (cudaStream_t)stream>>>(a);
   return launch_status();
 }
 

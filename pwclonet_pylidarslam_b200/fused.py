@@ -109,7 +109,7 @@ def _n_layers(sd, prefix):
 
 class FusedPWCLONet:
     def __init__(self, net):
-        sd = {k: v.detach() for k, v in net.state_dict().items()}
+        sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}   # fold BN on the host, once
         dev = next(net.parameters()).device
         if dev.type != "cuda":
             raise _lib.PwcloError("the fused PWCLO-Net engine needs the parameters on a CUDA device (no CPU fallback)")
@@ -166,10 +166,11 @@ class FusedPWCLONet:
         self.L = {k: A.layers(v) for k, v in self.recs.items() if isinstance(v, list)}
         self.lib = _lib.lib()
         self.launches = 0
+        self.verbose_timeline = False
         self.timeline = None     # when a list: (kernel name, start event, end event) per launch
 
     # ------------------------------------------------------------------ thin launch helpers
-    def _call(self, name, *args):
+    def _call(self, name, *args, note=""):
         if self.timeline is not None:
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
@@ -178,7 +179,7 @@ class FusedPWCLONet:
         self.launches += 1
         if self.timeline is not None:
             e.record()
-            self.timeline.append((name, s, e))
+            self.timeline.append((name + note, s, e))
 
     def _new(self, *shape, dtype=torch.float32):
         return torch.empty(shape, dtype=dtype, device=self.device)
@@ -186,7 +187,8 @@ class FusedPWCLONet:
     def fps(self, xyz, m):
         B, N, _ = xyz.shape
         idx = self._new(B, m, dtype=torch.int32)
-        self._call("pwclo_furthest_point_sampling", _p(xyz), B, N, m, 1, _p(idx))
+        self._call("pwclo_furthest_point_sampling", _p(xyz), B, N, m, 1, _p(idx),
+                   note=f"[B{B} N{N} m{m}]" if self.verbose_timeline else "")
         return idx
 
     def gather3(self, xyz, idx):
@@ -200,8 +202,14 @@ class FusedPWCLONet:
         S = queries.shape[1]
         idx = self._new(B, S, k, dtype=torch.int32)
         warped = self._new(B, S, 3) if warp_qt is not None else None
-        self._call("pwclo_knn", _p(xyz), _p(queries), B, N, S, k, _ext.KNN_SUM_ORDER, _p(warp_qt), _p(warped), _p(idx),
-                   None)
+        ws_bytes = self.lib.pwclo_knn_workspace_bytes(B, N) if _ext.KNN_SORTED and N >= _ext.KNN_SORTED_MIN_N else 0
+        if ws_bytes:
+            ws = self._new(ws_bytes, dtype=torch.uint8)
+            self._call("pwclo_knn_sorted", _p(xyz), _p(queries), B, N, S, k, _ext.KNN_SUM_ORDER, _p(warp_qt), _p(warped),
+                       _p(idx), None, _p(ws), ws_bytes, note=f"[B{B} S{S} N{N} k{k}]" if self.verbose_timeline else "")
+        else:
+            self._call("pwclo_knn", _p(xyz), _p(queries), B, N, S, k, _ext.KNN_SUM_ORDER, _p(warp_qt), _p(warped), _p(idx),
+                       None)
         return (idx, warped) if warp_qt is not None else idx
 
     def set_conv(self, key, xyz, feats, new_xyz, idx):
@@ -210,7 +218,8 @@ class FusedPWCLONet:
         layers = self.L[key]
         out = self._new(B, S, layers[len(layers) - 1].cout)
         C = feats.shape[2] if feats is not None else 3
-        self._call("pwclo_set_conv", _p(xyz), _p(feats), _p(new_xyz), _p(idx), B, N, S, K, C, layers, len(layers), _p(out))
+        self._call("pwclo_set_conv", _p(xyz), _p(feats), _p(new_xyz), _p(idx), B, N, S, K, C, layers, len(layers), _p(out),
+                   note=f"[{key} B{B} S{S} K{K} C{C}]" if self.verbose_timeline else "")
         return out
 
     def pointwise(self, key, srcs):
@@ -227,10 +236,12 @@ class FusedPWCLONet:
         N, C = xyz2.shape[1], f1.shape[2]
         e1 = self._new(B, S, 64)
         self._call("pwclo_cost_volume_1", _p(wxyz), _p(f1), _p(xyz2), _p(f2), _p(idx_q), B, S, N, idx_q.shape[2], C,
-                   self.L[prefix + ".mlp_convs"], self.L[prefix + ".mlp_conv_xyz_1"], self.L[prefix + ".mlp2_convs"], _p(e1))
+                   self.L[prefix + ".mlp_convs"], self.L[prefix + ".mlp_conv_xyz_1"], self.L[prefix + ".mlp2_convs"], _p(e1),
+                   note=f"[B{B} S{S} K{idx_q.shape[2]} C{C}]" if self.verbose_timeline else "")
         out = self._new(B, S, 64)
         self._call("pwclo_cost_volume_2", _p(wxyz), _p(f1), _p(e1), _p(idx_self), B, S, idx_self.shape[2], C,
-                   self.L[prefix + ".mlp_conv_xyz_2"], self.L[prefix + ".mlp3_convs"], _p(out))
+                   self.L[prefix + ".mlp_conv_xyz_2"], self.L[prefix + ".mlp3_convs"], _p(out),
+                   note=f"[B{B} S{S} C{C}]" if self.verbose_timeline else "")
         return out, e1
 
     def pose_head(self, prefix, emb, mask, coarse_qt, pose_params, level):
@@ -305,6 +316,7 @@ class FusedPWCLONet:
                 qt = self.pose_head(f"{p}.pose_calculator", ef, em, qt, pose, l - 1)
                 if trace is not None:
                     trace.update({f"pwr{l}.up_f": cf, f"pwr{l}.up_m": cm, f"pwr{l}.warped": warped, f"pwr{l}.cv": res,
-                                  f"pwr{l}.emb": ef, f"pwr{l}.mask": em, f"pwr{l}.qt": qt, f"pwr{l}.idx_q": idx_q})
+                                  f"pwr{l}.emb": ef, f"pwr{l}.mask": em, f"pwr{l}.qt": qt, f"pwr{l}.idx_q": idx_q,
+                                  f"pwr{l}.idx_s": idx_s})
                 emb_prev, mask_prev = ef, em
         return pose, mask_prev.permute(0, 2, 1), X1[1]

@@ -74,11 +74,23 @@ def test_pose_warp_refinement(run, l):
     t, pt = run["trace"], run["port"].trace
     # the warped cloud inherits the coarse pose's rounding noise (|dq| ~ 1e-6 at |p| ~ 30 m): 1e-4 m budget
     np.testing.assert_allclose(_cm(t[f"pwr{l}.warped"]), pt[f"pwr{l}.warped"].numpy(), rtol=0, atol=C.TOL_TRANSLATION_M)
-    # ... and so may a handful of near-tied neighbour decisions; everything else must be identical
-    same = (t[f"pwr{l}.idx_q"].cpu().numpy() == pt[f"pwr{l}.cv.idx_q"].numpy()).all(-1).mean()
-    assert same >= 0.995, same
-    for key, pkey in (("up_f", "up_f.out"), ("up_m", "up_m.out"), ("cv", "cv.out"), ("emb", "emb"), ("mask", "mask")):
+    # ... and so may a handful of near-tied neighbour decisions.  A point's cost-volume output depends on
+    # its own two neighbour lists and on the first-stage embedding of its self-neighbours: compare features
+    # on the points whose whole dependency set is identical (must be >= 98 % of them).
+    iq, iqr = t[f"pwr{l}.idx_q"].cpu().numpy(), pt[f"pwr{l}.cv.idx_q"].numpy()
+    isf, isr = t[f"pwr{l}.idx_s"].cpu().numpy(), pt[f"pwr{l}.cv.idx_self"].numpy()
+    same_q = (iq == iqr).all(-1)
+    assert same_q.mean() >= 0.995, same_q.mean()
+    same_s = (isf == isr).all(-1)
+    ok = same_q & same_s & np.stack([same_q[b][isr[b]].all(-1) for b in range(isr.shape[0])])
+    assert ok.mean() >= 0.98, ok.mean()
+    for key, pkey in (("up_f", "up_f.out"), ("up_m", "up_m.out")):
         e = C.rel_err(_cm(t[f"pwr{l}.{key}"]), pt[f"pwr{l}.{pkey}"].numpy())
+        assert e <= C.TOL_FEATURE_REL, (l, key, e)
+    for key, pkey in (("cv", "cv.out"), ("emb", "emb"), ("mask", "mask")):
+        got, want = _cm(t[f"pwr{l}.{key}"]), pt[f"pwr{l}.{pkey}"].numpy()
+        scale = np.abs(want).max()
+        e = max(np.abs(got[b][:, ok[b]] - want[b][:, ok[b]]).max() for b in range(got.shape[0])) / scale
         assert e <= C.TOL_FEATURE_REL, (l, key, e)
     qt = t[f"pwr{l}.qt"].cpu().numpy()
     np.testing.assert_allclose(qt[:, :4], pt[f"pwr{l}.q"].numpy(), rtol=0, atol=1e-5)

@@ -104,6 +104,25 @@ def test_knn_vs_oracle_bit_exact(cuda, B, N, S, K, order):
     np.testing.assert_array_equal(got_i.cpu().numpy(), want_i)
 
 
+@pytest.mark.parametrize("B,N,S,K", [(2, 8192, 2048, 32), (3, 2048, 1024, 8), (2, 1000, 333, 6), (2, 100, 64, 32), (1, 64, 7, 4)])
+def test_knn_sorted_equals_bruteforce(cuda, B, N, S, K):
+    """the sorted-slab search must be bit-identical to the brute-force kernel (same keys, exact pruning)"""
+    lid = np.stack([synthetic.make_pair(synthetic.SEED_BASE + 60 + i, 8192)["pc2"][:N] for i in range(B)])
+    rng = np.random.default_rng(3)
+    for xyz in (lid, _rand_cloud(rng, B, N), np.round(_rand_cloud(rng, B, N, 3.0))):   # lidar, gaussian, lattice (ties)
+        x = _dev(xyz, cuda)
+        q = x[:, :S].contiguous() + 0.0
+        old = _ext.KNN_SORTED
+        try:
+            _ext.KNN_SORTED = True
+            i1, d1 = _ext.knn(x, q, K, return_dist=True)
+            _ext.KNN_SORTED = False
+            i0, d0 = _ext.knn(x, q, K, return_dist=True)
+        finally:
+            _ext.KNN_SORTED = old
+        assert torch.equal(d1, d0) and torch.equal(i1, i0)
+
+
 def _tie_aware_equal(got_i, ref_i, ref_d):
     """torch.topk leaves the order among equal distances unspecified: indices must agree wherever
     the reference distance is unique inside the row, and as sets inside groups of equal distance."""
