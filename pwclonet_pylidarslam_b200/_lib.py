@@ -38,6 +38,11 @@ SIGNATURES = {
     "pwclo_cost_volume_1": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _LP, _LP, _LP, _vp, _vp],
     "pwclo_cost_volume_2": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _LP, _LP, _vp, _vp],
     "pwclo_pose_head": [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "pwclo_set_conv_tc": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _LP, _i, _vp, _vp],
+    "pwclo_pointwise_mlp_tc": [ctypes.POINTER(_vp), ctypes.POINTER(_i), _i, _i, _LP, _i, _vp, _vp],
+    "pwclo_cost_volume_1_tc": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _LP, _LP, _LP, _vp, _vp],
+    "pwclo_cost_volume_2_tc": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _LP, _LP, _vp, _vp],
+    "pwclo_tc_selftest": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "pwclo_gather_rows3": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "pwclo_transpose": [_vp, _i, _i, _i, _i, _vp, _vp],
 }

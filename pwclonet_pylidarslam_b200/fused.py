@@ -17,7 +17,9 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _ext, _lib
+import os
+
+from . import _ext, _lib, tc_pack
 
 BN_EPS = 1e-5
 
@@ -118,26 +120,41 @@ class FusedPWCLONet:
         self.A = A
         self.recs = {}
 
-        def mlp(prefix, first_order=None, first_k4=None):
-            recs = []
+        self.tc_recs = {}
+
+        def mlp(prefix, first_order=None, first_k4=None, tc_first_order=None):
+            recs, tcr = [], []
             for i in range(_n_layers(sd, prefix)):
                 W, b = fold_conv_bn(sd, f"{prefix}.layer{i}")
                 recs.append(A.add_layer(pack_layer(W, b, first_order if i == 0 else None, first_k4 if i == 0 else None)))
+                if W.shape[0] in (64, 128):       # tensor-core packing (tcgen05 kernels need cout 64 / 128)
+                    Wn = W.numpy()
+                    if i == 0 and tc_first_order is not None:
+                        Wi = np.zeros((Wn.shape[0], len(tc_first_order)))
+                        for dst, src in enumerate(tc_first_order):
+                            if src >= 0:
+                                Wi[:, dst] = Wn[:, src]
+                        Wn = Wi
+                    tcr.append({"w_off": A.add(tc_pack.pack_tc(Wn)), "b_off": A.add(b.float().numpy()),
+                                "cin": W.shape[1], "cout": W.shape[0]})
             self.recs[prefix] = recs
+            if len(tcr) == len(recs):
+                self.tc_recs[prefix] = tcr
 
         def sa_order(cin):  # reference (xyz_diff(3), feat(C)) -> internal (feat(C), xyz_diff(3))
             return list(range(3, cin)) + [0, 1, 2]
 
         for name in ("psa_1", "psa_2", "psa_3", "psa_4", "flow_feature_encoding"):
             cin = sd[f"{name}.mlp_module.layer0.conv.weight"].shape[1]
-            mlp(f"{name}.mlp_module", sa_order(cin))
+            mlp(f"{name}.mlp_module", sa_order(cin), tc_first_order=sa_order(cin) + [-1] * 5)
 
         def cost_volume(prefix):
             cin = sd[f"{prefix}.mlp_convs.layer0.conv.weight"].shape[1]
             order = list(range(10)) + [-1, -1] + list(range(10, cin))     # (geo(10), 0, 0, f1, f2)
-            mlp(f"{prefix}.mlp_convs", order)
-            mlp(f"{prefix}.mlp_conv_xyz_1")
-            mlp(f"{prefix}.mlp_conv_xyz_2")
+            geo_tc = list(range(10)) + [-1] * 6
+            mlp(f"{prefix}.mlp_convs", order, tc_first_order=list(range(10, cin)) + geo_tc)   # (f1, f2, geo(10), 0 x6)
+            mlp(f"{prefix}.mlp_conv_xyz_1", tc_first_order=geo_tc)
+            mlp(f"{prefix}.mlp_conv_xyz_2", tc_first_order=geo_tc)
             mlp(f"{prefix}.mlp2_convs")
             mlp(f"{prefix}.mlp3_convs")
 
@@ -155,7 +172,8 @@ class FusedPWCLONet:
         for l in (3, 2, 1):
             p = f"pose_warp_refinement_{l}"
             for up in ("setupconv_features", "setupconv_mask"):
-                mlp(f"{p}.{up}.mlp")          # reference order (features, xyz_diff) == internal order
+                cin_up = sd[f"{p}.{up}.mlp.layer0.conv.weight"].shape[1]
+                mlp(f"{p}.{up}.mlp", tc_first_order=list(range(cin_up)) + [-1] * 5)   # (features, xyz_diff) + pad
                 mlp(f"{p}.{up}.post_mlp")
             cost_volume(f"{p}.cost_volume")
             mlp(f"{p}.flow_predictor_features.mlp_convs")
@@ -164,6 +182,8 @@ class FusedPWCLONet:
             pose_calc(f"{p}.pose_calculator")
         A.finalize(dev)
         self.L = {k: A.layers(v) for k, v in self.recs.items() if isinstance(v, list)}
+        self.LT = {k: A.layers(v) for k, v in self.tc_recs.items()}
+        self.use_tc = os.environ.get("PWCLO_TC", "1") != "0"
         self.lib = _lib.lib()
         self.launches = 0
         self.verbose_timeline = False
@@ -218,6 +238,11 @@ class FusedPWCLONet:
         layers = self.L[key]
         out = self._new(B, S, layers[len(layers) - 1].cout)
         C = feats.shape[2] if feats is not None else 3
+        if self.use_tc and key in self.LT and feats is not None and C % 16 == 0:
+            tl = self.LT[key]
+            self._call("pwclo_set_conv_tc", _p(xyz), _p(feats), _p(new_xyz), _p(idx), B, N, S, K, C, tl, len(tl), _p(out),
+                       note=f"[{key} B{B} S{S} K{K} C{C}]" if self.verbose_timeline else "")
+            return out
         self._call("pwclo_set_conv", _p(xyz), _p(feats), _p(new_xyz), _p(idx), B, N, S, K, C, layers, len(layers), _p(out),
                    note=f"[{key} B{B} S{S} K{K} C{C}]" if self.verbose_timeline else "")
         return out
@@ -228,6 +253,10 @@ class FusedPWCLONet:
         out = self._new(srcs[0].shape[0], srcs[0].shape[1], layers[len(layers) - 1].cout)
         ptrs = (_vp * len(srcs))(*[s.data_ptr() for s in srcs])
         chans = (_i * len(srcs))(*[s.shape[2] for s in srcs])
+        if self.use_tc and key in self.LT and all(s.shape[2] % 16 == 0 for s in srcs):
+            tl = self.LT[key]
+            self._call("pwclo_pointwise_mlp_tc", ptrs, chans, len(srcs), rows, tl, len(tl), _p(out))
+            return out
         self._call("pwclo_pointwise_mlp", ptrs, chans, len(srcs), rows, layers, len(layers), _p(out))
         return out
 
@@ -235,6 +264,16 @@ class FusedPWCLONet:
         B, S, _ = wxyz.shape
         N, C = xyz2.shape[1], f1.shape[2]
         e1 = self._new(B, S, 64)
+        if self.use_tc:
+            note1 = f"[B{B} S{S} K{idx_q.shape[2]} C{C}]" if self.verbose_timeline else ""
+            self._call("pwclo_cost_volume_1_tc", _p(wxyz), _p(f1), _p(xyz2), _p(f2), _p(idx_q), B, S, N, idx_q.shape[2], C,
+                       self.LT[prefix + ".mlp_convs"], self.LT[prefix + ".mlp_conv_xyz_1"], self.LT[prefix + ".mlp2_convs"],
+                       _p(e1), note=note1)
+            out = self._new(B, S, 64)
+            self._call("pwclo_cost_volume_2_tc", _p(wxyz), _p(f1), _p(e1), _p(idx_self), B, S, idx_self.shape[2], C,
+                       self.LT[prefix + ".mlp_conv_xyz_2"], self.LT[prefix + ".mlp3_convs"], _p(out),
+                       note=f"[B{B} S{S} C{C}]" if self.verbose_timeline else "")
+            return out, e1
         self._call("pwclo_cost_volume_1", _p(wxyz), _p(f1), _p(xyz2), _p(f2), _p(idx_q), B, S, N, idx_q.shape[2], C,
                    self.L[prefix + ".mlp_convs"], self.L[prefix + ".mlp_conv_xyz_1"], self.L[prefix + ".mlp2_convs"], _p(e1),
                    note=f"[B{B} S{S} K{idx_q.shape[2]} C{C}]" if self.verbose_timeline else "")

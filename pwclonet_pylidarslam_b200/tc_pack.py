@@ -1,0 +1,32 @@
+"""Host-side packing of folded weights for the tcgen05 (3xTF32) layer kernels.
+
+A weight matrix W [N, K] (N outputs, K inputs, K-major like a torch conv weight) is split into
+tf32-exact hi / lo parts and stored chunk-wise in the canonical K-major no-swizzle shared-memory
+layout of the UMMA descriptor: [K/32 chunks][hi, lo][N/8][k/4 (8)][n%8 (8)][k%4 (4)] fp32, so that a
+chunk (32 input channels, hi+lo) is ONE contiguous TMA bulk copy and one MMA B operand per 8 inputs.
+"""
+import numpy as np
+
+
+def split_tf32(w):
+    w = np.ascontiguousarray(w, np.float32)
+    hi = (w.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    lo = (w - hi).astype(np.float32)
+    return hi, lo
+
+
+def pack_tc(W):
+    """W [N, K] float -> flat fp32 array, K zero-padded to a multiple of 32, N must be a multiple of 8."""
+    W = np.asarray(W, np.float64)
+    N, K = W.shape
+    assert N % 8 == 0
+    K32 = (K + 31) // 32 * 32
+    Wp = np.zeros((N, K32), np.float32)
+    Wp[:, :K] = W.astype(np.float32)
+    hi, lo = split_tf32(Wp)
+    out = np.empty((K32 // 32, 2, N // 8, 8, 8, 4), np.float32)
+    for part, m in enumerate((hi, lo)):
+        # m[n, k] -> [chunk, n/8, k/4 within chunk, n%8, k%4]
+        v = m.reshape(N // 8, 8, K32 // 32, 8, 4)          # [n/8, n%8, chunk, kc, k%4]
+        out[:, part] = v.transpose(2, 0, 3, 1, 4)
+    return out.reshape(-1)

@@ -72,8 +72,10 @@ def test_cost_volume_and_level4(run):
 @pytest.mark.parametrize("l", [3, 2, 1])
 def test_pose_warp_refinement(run, l):
     t, pt = run["trace"], run["port"].trace
-    # the warped cloud inherits the coarse pose's rounding noise (|dq| ~ 1e-6 at |p| ~ 30 m): 1e-4 m budget
-    np.testing.assert_allclose(_cm(t[f"pwr{l}.warped"]), pt[f"pwr{l}.warped"].numpy(), rtol=0, atol=C.TOL_TRANSLATION_M)
+    # the warped cloud inherits the coarse pose's rounding noise: the pose tolerances (1e-5 rad, 1e-4 m)
+    # propagate to |p| * 1e-5 + 1e-4 <= 5.2e-4 m for points within the 30 m crop (|p| <= 42 m)
+    np.testing.assert_allclose(_cm(t[f"pwr{l}.warped"]), pt[f"pwr{l}.warped"].numpy(), rtol=0,
+                               atol=42.0 * C.TOL_ROTATION_RAD + C.TOL_TRANSLATION_M)
     # ... and so may a handful of near-tied neighbour decisions.  A point's cost-volume output depends on
     # its own two neighbour lists and on the first-stage embedding of its self-neighbours: compare features
     # on the points whose whole dependency set is identical (must be >= 98 % of them).
