@@ -51,6 +51,24 @@ __device__ __forceinline__ void mbarrier_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   }
 }
+// polling variant with back-off: for the many waiters of a long phase, so that they do not steal
+// issue slots from the single MMA-issuing / TMA-issuing warps that share their scheduler
+__device__ __forceinline__ void mbarrier_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+  }
+}
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_addr(dst_smem)),

@@ -1,13 +1,15 @@
 // Tensor-core (tcgen05 / TMEM) versions of the fused PWCLO-Net layer kernels.
 //
 // One CTA = one 128-row tile (rows = points x neighbours), persistent over tiles.  Warp roles:
-//   warps 0-3  "row" warps: thread r owns tile row r == TMEM lane r.  They gather the layer input
-//              straight into TMEM (split into tf32-exact hi / lo planes), run every epilogue
+//   warps 0-15 "row" warps: warp w serves TMEM lane quadrant w % 4 (tile rows 32*(w%4) .. +31, one row
+//              per lane) and column slice w / 4 (every 4th group of 16 columns), so four warps share
+//              a quadrant and hide each other's TMEM / global latencies.  They gather the layer
+//              input straight into TMEM (split into tf32-exact hi / lo planes), run every epilogue
 //              (TMEM accumulator -> +bias -> ReLU -> hi/lo planes of the next layer and/or an fp32
 //              copy in shared memory) and the final pooling over the neighbour axis;
-//   warp 4     TMA producer: streams the packed hi/lo weight chunks (32 input channels each) of
+//   warp 16    TMA producer: streams the packed hi/lo weight chunks (32 input channels each) of
 //              every layer through a 3-slot shared-memory ring with cp.async.bulk + mbarriers;
-//   warp 5     MMA issuer: one thread issues tcgen05.mma.kind::tf32 with the A operand in TMEM and
+//   warp 17    MMA issuer: one thread issues tcgen05.mma.kind::tf32 with the A operand in TMEM and
 //              the B operand in shared memory: D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (3xTF32,
 //              fp32-class accuracy), accumulator in TMEM; tcgen05.commit releases ring slots and
 //              signals the epilogue.
@@ -16,6 +18,7 @@
 // TMEM column map (512 columns x 128 lanes): HI plane [0,192), LO plane [192,384), D [384,512).
 #include <math_constants.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "tc_mma.cuh"
@@ -23,7 +26,9 @@
 namespace pwclo {
 
 constexpr int TC_ROWS = 128;
-constexpr int TC_THREADS = 192;
+constexpr int TC_SLICES = 4;                      // row warps per TMEM lane quadrant (column slices)
+constexpr int TC_ROW_THREADS = 128 * TC_SLICES;   // 16 row warps: warp w -> quadrant w % 4, slice w / 4
+constexpr int TC_THREADS = TC_ROW_THREADS + 64;   // + TMA producer warp + MMA issuer warp
 constexpr int TC_SLOTS = 3;
 constexpr int TC_SLOT_FLOATS = 2 * 128 * 32;   // hi + lo chunk of a 128-wide layer (32 KB)
 constexpr int COL_HI = 0, COL_LO = 192, COL_D = 384;
@@ -55,13 +60,42 @@ struct TcArgs {
   int B, N, S, K, C;      // PW: S = total rows, K = 1
   int ldS0, ldS1;
   int nlayers;
+  int debug;              // bit 0: skip weight streaming (timing experiments only; results are garbage)
+  long long* dbg;         // optional per-phase clock64 stamps of CTA 0, tile 1 (profiling aid)
   TcLayer l[TC_MAX_LAYERS];
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+// 32-bit shared-window addresses are computed ONCE per kernel: converting a generic pointer inside a
+// loop costs an S2UR SR_CgaCtaId (hundreds of cycles) per use.
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void rows_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void rows_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_ROW_THREADS) : "memory"); }
 
 // write 16 consecutive fp32 values of this thread's row into the hi/lo planes at column `col`
 __device__ __forceinline__ void plane_store16(uint32_t lane_base, int col, const float (&v)[16]) {
@@ -96,21 +130,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const TcArgs a, i
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (warp == 5) tmem_alloc(&tmem_base_s, 512);
+  if (warp == TC_ROW_THREADS / 32 + 1) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int s = 0; s < TC_SLOTS; ++s) { mbarrier_init(&full_bar[s], 1); mbarrier_init(&empty_bar[s], 1); }
     mbarrier_init(&d_ready, 1);
-    mbarrier_init(&a_ready, TC_ROWS);
+    mbarrier_init(&a_ready, TC_ROW_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tb = tmem_base_s;
+  const uint32_t full_a = smem_addr(&full_bar[0]), empty_a = smem_addr(&empty_bar[0]);   // + 8 * slot
+  const uint32_t dready_a = smem_addr(&d_ready), aready_a = smem_addr(&a_ready);
+  const uint32_t ring_addr = smem_addr(ring);
 
-  if (warp == 4) {
+  if (warp == TC_ROW_THREADS / 32) {
     // ============================== TMA producer ==============================
-    if (lane == 0) {
+    if (lane == 0 && !(a.debug & 1)) {
       uint32_t use = 0;   // global chunk counter
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int L = 0; L < a.nlayers; ++L) {
@@ -121,63 +158,82 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const TcArgs a, i
           for (int ch = 0; ch < nchunk; ++ch, ++use) {
             const int s = use % TC_SLOTS;
             const uint32_t n = use / TC_SLOTS;          // how many times this slot was filled before
-            if (n > 0) mbarrier_wait(&empty_bar[s], (n - 1) & 1);
-            mbarrier_expect_tx(&full_bar[s], bytes);
-            tma_bulk_g2s(ring + (size_t)s * TC_SLOT_FLOATS, ly.w + (size_t)ch * 2 * ly.n * 32, bytes, &full_bar[s]);
+            if (n > 0) mbar_wait_a(empty_a + 8 * s, (n - 1) & 1);
+            mbar_expect_tx_a(full_a + 8 * s, bytes);
+            tma_bulk_g2s_a(ring_addr + s * (uint32_t)(TC_SLOT_FLOATS * sizeof(float)), ly.w + (size_t)ch * 2 * ly.n * 32, bytes,
+                           full_a + 8 * s);
           }
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == TC_ROW_THREADS / 32 + 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      uint32_t use = 0, a_cnt = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int L = 0; L < a.nlayers; ++L) {
-          const TcLayer& ly = a.l[L];
-          const int ksteps = (ly.seg_n[0] + ly.seg_n[1]) >> 3;
-          const int ks0 = ly.seg_n[0] >> 3;
-          const uint32_t idesc = tc_idesc_tf32(128, ly.n);
-          mbarrier_wait(&a_ready, a_cnt & 1);     // the A planes of this layer are complete
+    // The whole warp walks the (warp-uniform) schedule so that descriptors and TMEM addresses stay in
+    // uniform registers; only the tcgen05 instructions themselves are issued by the elected lane.
+    const bool leader = lane == 0;
+    constexpr uint64_t DESC_FIXED = (8ull << 16) | (64ull << 32) | (1ull << 46);   // LBO 128 B, SBO 1024 B, sm100
+    uint32_t use = 0, a_cnt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int L = 0; L < a.nlayers; ++L) {
+        {
+          const int n = a.l[L].n;
+          const int col0 = a.l[L].seg_col[0], col1 = a.l[L].seg_col[1];
+          const int ks0 = a.l[L].seg_n[0] >> 3;
+          const int ksteps = ks0 + (a.l[L].seg_n[1] >> 3);
+          const uint32_t idesc = tc_idesc_tf32(128, n);
+          const uint32_t lo_off = (uint32_t)n * 128u;           // byte offset of the lo half of a chunk
+          mbar_wait_a(aready_a, a_cnt & 1);                     // the A planes of this layer are complete
           ++a_cnt;
           tc_fence_after();
+          const bool mstamp = a.dbg != nullptr && blockIdx.x == 0 && tile == (int)gridDim.x && leader;
+          if (mstamp) a.dbg[32 + 2 * L] = clock64();
           uint32_t acc = 0;
           for (int k0 = 0; k0 < ksteps; k0 += 4, ++use) {
-            const int s = use % TC_SLOTS;
-            mbarrier_wait(&full_bar[s], (use / TC_SLOTS) & 1);
+            const uint32_t s = use % TC_SLOTS;
+            if (!(a.debug & 1)) mbar_wait_a(full_a + 8 * s, (use / TC_SLOTS) & 1);
             tc_fence_after();
-            const float* bh = ring + (size_t)s * TC_SLOT_FLOATS;
-            const float* bl = bh + ly.n * 32;
+            const uint32_t slot = ring_addr + s * (uint32_t)(TC_SLOT_FLOATS * sizeof(float));
+            const uint64_t dh0 = DESC_FIXED | (uint64_t)((slot & 0x3ffffu) >> 4);
+            const uint64_t dl0 = DESC_FIXED | (uint64_t)(((slot + lo_off) & 0x3ffffu) >> 4);
             const int kn = min(4, ksteps - k0);
-            for (int j = 0; j < kn; ++j) {
-              const int ks = k0 + j;
-              const int col = ks < ks0 ? ly.seg_col[0] + 8 * ks : ly.seg_col[1] + 8 * (ks - ks0);
-              const uint64_t dh = tc_smem_desc(bh + j * 64), dl = tc_smem_desc(bl + j * 64);
-              tc_mma_ts(tb + COL_D, tb + COL_HI + col, dh, idesc, acc);
-              tc_mma_ts(tb + COL_D, tb + COL_LO + col, dh, idesc, 1);
-              tc_mma_ts(tb + COL_D, tb + COL_HI + col, dl, idesc, 1);
-              acc = 1;
+            // A-operand column of the first k-step of this chunk; a chunk never straddles the two segments
+            // unless ks0 % 4 != 0, which the per-step select below handles
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < kn) {
+                const int ks = k0 + j;
+                const uint32_t col = (uint32_t)(ks < ks0 ? col0 + 8 * ks : col1 + 8 * (ks - ks0));
+                const uint64_t dh = dh0 + (uint64_t)(16 * j), dl = dl0 + (uint64_t)(16 * j);   // +256 B per k-step
+                tc_mma_ts_warp(tb + COL_D, tb + COL_HI + col, dh, idesc, acc);
+                tc_mma_ts_warp(tb + COL_D, tb + COL_LO + col, dh, idesc, 1);
+                tc_mma_ts_warp(tb + COL_D, tb + COL_HI + col, dl, idesc, 1);
+                acc = 1;
+              }
             }
-            tc_commit(&empty_bar[s]);             // slot reusable once these MMAs have read it
+            tc_commit_warp(empty_a + 8 * s);                    // slot reusable once these MMAs have read it
           }
-          tc_commit(&d_ready);                    // accumulator complete
+          tc_commit_warp(dready_a);                             // accumulator complete
+          if (mstamp) a.dbg[33 + 2 * L] = clock64();
         }
       }
     }
   } else {
     // ============================== row warps ==============================
-    const int r = tid;                             // tile row == TMEM lane
-    const uint32_t lane_base = tb + ((uint32_t)(warp * 32) << 16);
+    const int quad = warp & 3, slice = warp >> 2;
+    const int r = quad * 32 + lane;                // tile row == TMEM lane
+    const uint32_t lane_base = tb + ((uint32_t)(quad * 32) << 16);
     uint32_t d_cnt = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       // ---------------- gather the layer-0 input into the planes ----------------
-      int b = 0, p0 = 0, P = TC_ROWS;
+      // 16-column groups are dealt round-robin to the 4 slices of a quadrant (group counter `grp`)
+      int b = 0, p0 = 0, P = TC_ROWS, grp = 0;
       if (MODE == TC_PW) {
         const int row = min(tile * TC_ROWS + r, a.S - 1);
         int col = 0;
         for (int s = 0; s < a.nsrc; ++s) {
           const float* src = a.src[s] + (size_t)row * a.c_src[s];
-          for (int c = 0; c < a.c_src[s]; c += 16) {
+          for (int c = 0; c < a.c_src[s]; c += 16, ++grp) {
+            if ((grp & (TC_SLICES - 1)) != slice) continue;
             float v[16];
             load16(src + c, v);
             plane_store16(lane_base, col + c, v);
@@ -193,47 +249,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const TcArgs a, i
         const int gp = min(p0 + min(p, P - 1), a.S - 1);
         const int n = valid ? a.idx[((size_t)b * a.S + gp) * a.K + k] : 0;
         if (MODE == TC_SA) {
-          // planes: [feat(C) | xyz_nbr - xyz_ctr (3) + 5 zeros]
-          const float* q = a.xyz_ref + ((size_t)b * a.N + n) * 3;
-          const float* ctr = a.xyz_ctr + ((size_t)b * a.S + gp) * 3;
+          // planes: [feat(C) | xyz_nbr - xyz_ctr (3) + zeros]
           const float* f = a.f_ref + ((size_t)b * a.N + n) * a.C;
-          for (int c = 0; c < a.C; c += 16) {
+          for (int c = 0; c < a.C; c += 16, ++grp) {
+            if ((grp & (TC_SLICES - 1)) != slice) continue;
             float v[16];
             load16(f + c, v);
             plane_store16(lane_base, c, v);
           }
-          float v[16];
+          if ((grp & (TC_SLICES - 1)) == slice) {
+            const float* q = a.xyz_ref + ((size_t)b * a.N + n) * 3;
+            const float* ctr = a.xyz_ctr + ((size_t)b * a.S + gp) * 3;
+            float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0.f;
-          v[0] = __fsub_rn(q[0], ctr[0]); v[1] = __fsub_rn(q[1], ctr[1]); v[2] = __fsub_rn(q[2], ctr[2]);
-          plane_store16(lane_base, a.C, v);
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            v[0] = __fsub_rn(q[0], ctr[0]); v[1] = __fsub_rn(q[1], ctr[1]); v[2] = __fsub_rn(q[2], ctr[2]);
+            plane_store16(lane_base, a.C, v);
+          }
         } else if (MODE == TC_CV1) {
           // planes: [f1(C) | f2 nbr(C)] at 0, geo(10)+6 zeros at 176
           const float* f1 = a.f_ctr + ((size_t)b * a.S + gp) * a.C;
           const float* f2 = a.f_ref + ((size_t)b * a.N + n) * a.C;
-          for (int c = 0; c < a.C; c += 16) {
+          for (int c = 0; c < 2 * a.C; c += 16, ++grp) {
+            if ((grp & (TC_SLICES - 1)) != slice) continue;
             float v[16];
-            load16(f1 + c, v);
+            load16(c < a.C ? f1 + c : f2 + (c - a.C), v);
             plane_store16(lane_base, c, v);
-            load16(f2 + c, v);
-            plane_store16(lane_base, a.C + c, v);
           }
-          float g[16];
-          geo16(g, a.xyz_ctr + ((size_t)b * a.S + gp) * 3, a.xyz_ref + ((size_t)b * a.N + n) * 3);
-          plane_store16(lane_base, 176, g);
+          if ((grp & (TC_SLICES - 1)) == slice) {
+            float g[16];
+            geo16(g, a.xyz_ctr + ((size_t)b * a.S + gp) * 3, a.xyz_ref + ((size_t)b * a.N + n) * 3);
+            plane_store16(lane_base, 176, g);
+          }
         } else {  // TC_CV2
           // planes: geo(10)+6 zeros at 0 (consumed by the first layer), f1(C) at 64, e1 nbr(64) at 64+C
-          float g[16];
-          geo16(g, a.xyz_ctr + ((size_t)b * a.S + gp) * 3, a.xyz_ref + ((size_t)b * a.S + n) * 3);
-          plane_store16(lane_base, 0, g);
+          if (slice == 0) {
+            float g[16];
+            geo16(g, a.xyz_ctr + ((size_t)b * a.S + gp) * 3, a.xyz_ref + ((size_t)b * a.S + n) * 3);
+            plane_store16(lane_base, 0, g);
+          }
+          grp = 1;
           const float* f1 = a.f_ctr + ((size_t)b * a.S + gp) * a.C;
-          for (int c = 0; c < a.C; c += 16) {
+          for (int c = 0; c < a.C; c += 16, ++grp) {
+            if ((grp & (TC_SLICES - 1)) != slice) continue;
             float v[16];
             load16(f1 + c, v);
             plane_store16(lane_base, 64 + c, v);
           }
           const float* e1 = a.f_ref + ((size_t)b * a.S + n) * 64;
-          for (int c = 0; c < 64; c += 16) {
+          for (int c = 0; c < 64; c += 16, ++grp) {
+            if ((grp & (TC_SLICES - 1)) != slice) continue;
             float v[16];
             load16(e1 + c, v);
             plane_store16(lane_base, 64 + a.C + c, v);
@@ -243,18 +308,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const TcArgs a, i
           }
         }
       }
+      const bool stamp = a.dbg != nullptr && blockIdx.x == 0 && tile == (int)gridDim.x && tid == 0;
+      if (stamp) a.dbg[0] = clock64();
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&a_ready);
+      mbar_arrive_a(aready_a);
+      if (stamp) a.dbg[1] = clock64();
 
       // ---------------- layer epilogues ----------------
       for (int L = 0; L < a.nlayers; ++L) {
         const TcLayer& ly = a.l[L];
-        mbarrier_wait(&d_ready, d_cnt & 1);
+        mbar_wait_a(dready_a, d_cnt & 1);
         ++d_cnt;
         tc_fence_after();
+        if (stamp) a.dbg[2 + 2 * L] = clock64();
         float* sdst = ly.out_smem == 1 ? S0 + (size_t)r * a.ldS0 : (ly.out_smem == 2 ? S1 + (size_t)r * a.ldS1 : nullptr);
-        for (int c = 0; c < ly.n; c += 16) {
+        for (int c = slice * 16; c < ly.n; c += 16 * TC_SLICES) {
           float v[16];
           tmem_ld16(lane_base + COL_D + c, v);
 #pragma unroll
@@ -273,17 +342,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const TcArgs a, i
         if (L + 1 < a.nlayers) {
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(&a_ready);
+          mbar_arrive_a(aready_a);
         }
+        if (stamp) a.dbg[3 + 2 * L] = clock64();
       }
       tc_fence_before();
       rows_sync();   // S0 / S1 complete
+      if (stamp) a.dbg[20] = clock64();
 
       // ---------------- pooling over the neighbour axis / output ----------------
       const int co = a.l[a.nlayers - 1].n;
       if (MODE == TC_PW) {
         const int co4 = co >> 2;
-        for (int e = r; e < TC_ROWS * co4; e += TC_ROWS) {
+        for (int e = tid; e < TC_ROWS * co4; e += TC_ROW_THREADS) {
           const int rr = e / co4, c4 = e - rr * co4;
           const int row = tile * TC_ROWS + rr;
           if (row < a.S)
@@ -291,7 +362,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const TcArgs a, i
                 *reinterpret_cast<const float4*>(S0 + (size_t)rr * a.ldS0 + 4 * c4);
         }
       } else if (MODE == TC_SA) {
-        for (int e = r; e < P * co; e += TC_ROWS) {
+        for (int e = tid; e < P * co; e += TC_ROW_THREADS) {
           const int p = e / co, c = e - p * co;
           if (p0 + p >= a.S) continue;
           const float* y = S0 + (size_t)(p * a.K) * a.ldS0 + c;
@@ -300,7 +371,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const TcArgs a, i
           a.out[((size_t)b * a.S + p0 + p) * co + c] = m;
         }
       } else {
-        for (int e = r; e < P * 64; e += TC_ROWS) {
+        for (int e = tid; e < P * 64; e += TC_ROW_THREADS) {
           const int p = e >> 6, c = e & 63;
           if (p0 + p >= a.S) continue;
           const float* att = S0 + (size_t)(p * a.K) * a.ldS0 + c;
@@ -317,11 +388,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const TcArgs a, i
         }
       }
       rows_sync();   // pooling done before the next tile's epilogues overwrite S0 / S1
+      if (stamp) a.dbg[21] = clock64();
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tb, 512);
+  if (warp == TC_ROW_THREADS / 32 + 1) tmem_dealloc(tb, 512);
 }
 
 static bool tc_layer_set(TcLayer& L, const pwclo_layer_t& src, int col0, int n0, int col1, int n1, int out_col, int out_smem) {
@@ -337,6 +409,12 @@ static bool tc_layer_set(TcLayer& L, const pwclo_layer_t& src, int col0, int n0,
 template <int MODE>
 static int tc_launch(TcArgs& a, int ntiles, int tiles_per_cloud, cudaStream_t st) {
   if (a.ldS1 == 0) a.ldS1 = 4;
+  if (const char* d = getenv("PWCLO_TC_DEBUG")) a.debug = atoi(d);
+  static long long* dbg_buf = nullptr;
+  if (getenv("PWCLO_TC_STAMPS")) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
+    a.dbg = dbg_buf;
+  }
   const size_t smem = (size_t)TC_SLOTS * TC_SLOT_FLOATS * 4 + (size_t)TC_ROWS * (a.ldS0 + a.ldS1) * 4 + 1024;
   if (smem > 227 * 1024) return PWCLO_EUNSUPPORTED;
   auto kern = tc_mlp_kernel<MODE>;
@@ -344,6 +422,15 @@ static int tc_launch(TcArgs& a, int ntiles, int tiles_per_cloud, cudaStream_t st
   if (e != cudaSuccess) return (int)e;
   const int grid = min(ntiles, kNumSM);
   kern<<<grid, TC_THREADS, smem, st>>>(a, ntiles, tiles_per_cloud);
+  if (a.dbg) {
+    long long h[64];
+    cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tc stamps mode %d] gather_end +%lld arrive +%lld |", MODE, h[0] - h[0], h[1] - h[0]);
+    for (int L = 0; L < a.nlayers; ++L)
+      fprintf(stderr, " L%d: mma_start +%lld issued +%lld dready_seen +%lld epi_end +%lld |", L, h[32 + 2 * L] - h[0],
+              h[33 + 2 * L] - h[0], h[2 + 2 * L] - h[0], h[3 + 2 * L] - h[0]);
+    fprintf(stderr, " pooled_sync +%lld tile_end +%lld\n", h[20] - h[0], h[21] - h[0]);
+  }
   return launch_status();
 }
 

@@ -40,6 +40,29 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-collective variants: called by ALL lanes of the issuing warp with warp-uniform operands; one
+// elected lane issues.  Keeping the C++ control flow convergent lets ptxas hold descriptors and TMEM
+// addresses in uniform registers (no per-instruction R2UR / ELECT loops).
+__device__ __forceinline__ void tc_mma_ts_warp(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_warp(uint32_t bar_addr) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(bar_addr)
+      : "memory");
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
