@@ -190,7 +190,8 @@ class FusedPWCLONet:
         self.timeline = None     # when a list: (kernel name, start event, end event) per launch
 
     # ------------------------------------------------------------------ thin launch helpers
-    def _call(self, name, *args, note=""):
+    def _call(self, name, *args, note="", work=(0, 0)):
+        """work = (algorithmic HBM bytes, MLP flops) of this launch, recorded with the timeline"""
         if self.timeline is not None:
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
@@ -199,7 +200,10 @@ class FusedPWCLONet:
         self.launches += 1
         if self.timeline is not None:
             e.record()
-            self.timeline.append((name + note, s, e))
+            self.timeline.append((name + note, s, e, work))
+
+    def _flops(self, key, rows):
+        return 2 * rows * sum(r["cin"] * r["cout"] for r in self.recs[key])
 
     def _new(self, *shape, dtype=torch.float32):
         return torch.empty(shape, dtype=dtype, device=self.device)
@@ -208,7 +212,7 @@ class FusedPWCLONet:
         B, N, _ = xyz.shape
         idx = self._new(B, m, dtype=torch.int32)
         self._call("pwclo_furthest_point_sampling", _p(xyz), B, N, m, 1, _p(idx),
-                   note=f"[B{B} N{N} m{m}]" if self.verbose_timeline else "")
+                   note=f"[B{B} N{N} m{m}]" if self.verbose_timeline else "", work=(4 * B * (3 * N + m), 0))
         return idx
 
     def gather3(self, xyz, idx):
@@ -226,10 +230,11 @@ class FusedPWCLONet:
         if ws_bytes:
             ws = self._new(ws_bytes, dtype=torch.uint8)
             self._call("pwclo_knn_sorted", _p(xyz), _p(queries), B, N, S, k, _ext.KNN_SUM_ORDER, _p(warp_qt), _p(warped),
-                       _p(idx), None, _p(ws), ws_bytes, note=f"[B{B} S{S} N{N} k{k}]" if self.verbose_timeline else "")
+                       _p(idx), None, _p(ws), ws_bytes, note=f"[B{B} S{S} N{N} k{k}]" if self.verbose_timeline else "",
+                       work=(4 * B * (3 * S + 3 * N + S * k), 0))
         else:
             self._call("pwclo_knn", _p(xyz), _p(queries), B, N, S, k, _ext.KNN_SUM_ORDER, _p(warp_qt), _p(warped), _p(idx),
-                       None)
+                       None, work=(4 * B * (3 * S + 3 * N + S * k), 0))
         return (idx, warped) if warp_qt is not None else idx
 
     def set_conv(self, key, xyz, feats, new_xyz, idx):
@@ -241,10 +246,12 @@ class FusedPWCLONet:
         if self.use_tc and key in self.LT and feats is not None and C % 16 == 0:
             tl = self.LT[key]
             self._call("pwclo_set_conv_tc", _p(xyz), _p(feats), _p(new_xyz), _p(idx), B, N, S, K, C, tl, len(tl), _p(out),
-                       note=f"[{key} B{B} S{S} K{K} C{C}]" if self.verbose_timeline else "")
+                       note=f"[{key} B{B} S{S} K{K} C{C}]" if self.verbose_timeline else "",
+                       work=(4 * B * (S * K + S * out.shape[2] + N * (C + 3)), self._flops(key, B * S * K)))
             return out
         self._call("pwclo_set_conv", _p(xyz), _p(feats), _p(new_xyz), _p(idx), B, N, S, K, C, layers, len(layers), _p(out),
-                   note=f"[{key} B{B} S{S} K{K} C{C}]" if self.verbose_timeline else "")
+                   note=f"[{key} B{B} S{S} K{K} C{C}]" if self.verbose_timeline else "",
+                   work=(4 * B * (S * K + S * out.shape[2] + N * (C + 3)), self._flops(key, B * S * K)))
         return out
 
     def pointwise(self, key, srcs):
@@ -255,32 +262,39 @@ class FusedPWCLONet:
         chans = (_i * len(srcs))(*[s.shape[2] for s in srcs])
         if self.use_tc and key in self.LT and all(s.shape[2] % 16 == 0 for s in srcs):
             tl = self.LT[key]
-            self._call("pwclo_pointwise_mlp_tc", ptrs, chans, len(srcs), rows, tl, len(tl), _p(out))
+            self._call("pwclo_pointwise_mlp_tc", ptrs, chans, len(srcs), rows, tl, len(tl), _p(out),
+                       work=(4 * rows * (sum(s.shape[2] for s in srcs) + out.shape[2]), self._flops(key, rows)))
             return out
-        self._call("pwclo_pointwise_mlp", ptrs, chans, len(srcs), rows, layers, len(layers), _p(out))
+        self._call("pwclo_pointwise_mlp", ptrs, chans, len(srcs), rows, layers, len(layers), _p(out),
+                   work=(4 * rows * (sum(s.shape[2] for s in srcs) + out.shape[2]), self._flops(key, rows)))
         return out
 
     def cost_volume(self, prefix, wxyz, f1, xyz2, f2, idx_q, idx_self):
         B, S, _ = wxyz.shape
         N, C = xyz2.shape[1], f1.shape[2]
         e1 = self._new(B, S, 64)
+        Kq, Ks = idx_q.shape[2], idx_self.shape[2]
+        fl1 = sum(self._flops(prefix + k, B * S * Kq) for k in (".mlp_convs", ".mlp_conv_xyz_1", ".mlp2_convs"))
+        fl2 = sum(self._flops(prefix + k, B * S * Ks) for k in (".mlp_conv_xyz_2", ".mlp3_convs"))
+        w1 = (4 * B * (S * (3 + C + Kq + 64) + N * (3 + C)), fl1)
+        w2 = (4 * B * S * (3 + C + 64 + Ks + 64), fl2)
         if self.use_tc:
             note1 = f"[B{B} S{S} K{idx_q.shape[2]} C{C}]" if self.verbose_timeline else ""
             self._call("pwclo_cost_volume_1_tc", _p(wxyz), _p(f1), _p(xyz2), _p(f2), _p(idx_q), B, S, N, idx_q.shape[2], C,
                        self.LT[prefix + ".mlp_convs"], self.LT[prefix + ".mlp_conv_xyz_1"], self.LT[prefix + ".mlp2_convs"],
-                       _p(e1), note=note1)
+                       _p(e1), note=note1, work=w1)
             out = self._new(B, S, 64)
             self._call("pwclo_cost_volume_2_tc", _p(wxyz), _p(f1), _p(e1), _p(idx_self), B, S, idx_self.shape[2], C,
                        self.LT[prefix + ".mlp_conv_xyz_2"], self.LT[prefix + ".mlp3_convs"], _p(out),
-                       note=f"[B{B} S{S} C{C}]" if self.verbose_timeline else "")
+                       note=f"[B{B} S{S} C{C}]" if self.verbose_timeline else "", work=w2)
             return out, e1
         self._call("pwclo_cost_volume_1", _p(wxyz), _p(f1), _p(xyz2), _p(f2), _p(idx_q), B, S, N, idx_q.shape[2], C,
                    self.L[prefix + ".mlp_convs"], self.L[prefix + ".mlp_conv_xyz_1"], self.L[prefix + ".mlp2_convs"], _p(e1),
-                   note=f"[B{B} S{S} K{idx_q.shape[2]} C{C}]" if self.verbose_timeline else "")
+                   note=f"[B{B} S{S} K{idx_q.shape[2]} C{C}]" if self.verbose_timeline else "", work=w1)
         out = self._new(B, S, 64)
         self._call("pwclo_cost_volume_2", _p(wxyz), _p(f1), _p(e1), _p(idx_self), B, S, idx_self.shape[2], C,
                    self.L[prefix + ".mlp_conv_xyz_2"], self.L[prefix + ".mlp3_convs"], _p(out),
-                   note=f"[B{B} S{S} C{C}]" if self.verbose_timeline else "")
+                   note=f"[B{B} S{S} C{C}]" if self.verbose_timeline else "", work=w2)
         return out, e1
 
     def pose_head(self, prefix, emb, mask, coarse_qt, pose_params, level):

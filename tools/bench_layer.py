@@ -29,7 +29,7 @@ for _ in range(5):
     eng.cost_volume(prefix, wxyz, f1, xyz2, f2, idx_q, idx_s)
 torch.cuda.synchronize()
 acc = {}
-for name, s, e in eng.timeline:
+for name, s, e, _w in eng.timeline:
     acc.setdefault(name, []).append(s.elapsed_time(e))
 for k, v in acc.items():
     print(f"{k}: {sorted(v)[len(v) // 2]:.4f} ms  (B{B} S{S} N{N} K{K} C{C}, debug={os.environ.get('PWCLO_TC_DEBUG', '0')})")

@@ -25,7 +25,7 @@ with torch.no_grad():
     net(d1, None, d2, None)
 torch.cuda.synchronize()
 tot = 0.0
-for name, s, e in eng.timeline:
+for name, s, e, _w in eng.timeline:
     ms = s.elapsed_time(e)
     tot += ms
     print(f"{ms:8.3f} ms  {name}")
