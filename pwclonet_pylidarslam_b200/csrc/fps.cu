@@ -13,6 +13,8 @@
 //     reference, and exact ties are resolved exactly like the reference's tree: the candidate with
 //     the smallest (bit-reversed (k mod T), k) wins, T = the reference's block size for this n
 //     (EXT/include/cuda_utils.h:13-19).  See DESIGN.md "FPS tie order".
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pwclo {
@@ -132,6 +134,230 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origin_ski
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Slab-skipping variant (same result, bit for bit).  The points of a cloud are re-dealt so that warp w
+// owns a contiguous slab along the cloud's widest axis.  A warp whose slab is farther from the point
+// selected last than its current largest running minimum cannot change any of its minima
+// (d >= fl(dx^2) >= fl(dmin^2) > max mind), so it skips the whole update and re-submits its cached
+// (value, key).  After the first ~100 rounds only the 2-4 slabs around the new sample do any work.
+// Inside a slab points are dealt to (lane, j) in ascending tie-key order, which keeps the per-thread
+// "first maximum wins" scan equivalent to the reference's tie order.
+// -------------------------------------------------------------------------------------------------
+typedef unsigned long long fu64;
+
+__device__ __forceinline__ unsigned fps_ordered_bits(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+template <int NP, int THREADS>
+__device__ __forceinline__ void fps_bitonic_sort(fu64* keys, int tid) {
+  for (int k = 2; k <= NP; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int t = tid; t < NP / 2; t += THREADS) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int hi = lo | j;
+        const fu64 a = keys[lo], c = keys[hi];
+        const bool up = (lo & k) == 0;
+        if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <int NP, int THREADS>
+__device__ __forceinline__ void fps_bitonic_sort32(unsigned* keys, int tid) {
+  for (int k = 2; k <= NP; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int t = tid; t < NP / 2; t += THREADS) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int hi = lo | j;
+        const unsigned a = keys[lo], c = keys[hi];
+        const bool up = (lo & k) == 0;
+        if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <int P, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+fps_slab_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origin_skip, int32_t* __restrict__ idx, int dbg) {
+  constexpr int NP = P * THREADS;
+  constexpr int NW = THREADS / 32;
+  extern __shared__ __align__(16) unsigned char fps_smem[];
+  unsigned* keys = reinterpret_cast<unsigned*>(fps_smem);         // [NP] (coarse axis coordinate, index) sort keys
+  int* sidx = reinterpret_cast<int*>(keys + NP);                  // [NP] sorted slot -> original index
+  float* sx = reinterpret_cast<float*>(sidx + NP);                // [n] original order
+  float* sy = sx + n;
+  float* sz = sy + n;
+  __shared__ unsigned red_val[2][32];
+  __shared__ unsigned red_key[2][32];
+  __shared__ float ext_mn[3][32], ext_mx[3][32];
+  __shared__ int axis_s;
+
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  xyz += (size_t)b * n * 3;
+  idx += (size_t)b * m;
+
+  // ---- stage the cloud, pick the widest axis
+  float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+  for (int k = tid; k < n; k += THREADS) {
+    const float x = xyz[k * 3 + 0], y = xyz[k * 3 + 1], z = xyz[k * 3 + 2];
+    sx[k] = x; sy[k] = y; sz[k] = z;
+    mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
+    mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
+    mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    for (int off = 16; off; off >>= 1) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(PWCLO_FULL_MASK, mn[d], off));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(PWCLO_FULL_MASK, mx[d], off));
+    }
+    if (lane == 0) { ext_mn[d][warp] = mn[d]; ext_mx[d][warp] = mx[d]; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float ext[3];
+    for (int d = 0; d < 3; ++d) {
+      float a = 3.4e38f, c = -3.4e38f;
+      for (int w = 0; w < NW; ++w) { a = fminf(a, ext_mn[d][w]); c = fmaxf(c, ext_mx[d][w]); }
+      ext[d] = c - a;
+    }
+    axis_s = (ext[0] >= ext[1] && ext[0] >= ext[2]) ? 0 : (ext[2] >= ext[1] ? 2 : 1);
+    idx[0] = 0;
+  }
+  __syncthreads();
+  const int axis = axis_s;
+  const float* sa = axis == 0 ? sx : (axis == 1 ? sy : sz);
+
+  // ---- sort 1 along the axis: key = (top 19 bits of the order-preserving coordinate, 13-bit index); the
+  // truncation only coarsens the slab assignment.  sort 2 by (slab, compact tie key): inside a slab the
+  // points are ordered by the reference's tie key, so that dealing them lane-major gives every thread
+  // its points in ascending tie-key order (the strict '>' scan then keeps the reference's tie order).
+  static_assert(NP <= 8192, "13-bit index field");
+  for (int i = tid; i < NP; i += THREADS)
+    keys[i] = i < n ? ((fps_ordered_bits(sa[i]) & 0xffffe000u) | (unsigned)i) : 0xffffffffu;
+  __syncthreads();
+  fps_bitonic_sort32<NP, THREADS>(keys, tid);
+  {
+    unsigned k2[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int i = tid + j * THREADS;
+      const unsigned k1 = keys[i];
+      const unsigned slab = (unsigned)(i / (32 * P));
+      // compact 13-bit tie key: bit-reversed (k mod T) above (k div T)
+      const unsigned k = k1 & 0x1fffu;
+      const unsigned ck = logT == 0 ? k : (((__brev(k & ((1u << logT) - 1u)) >> (32 - logT)) << (13 - logT)) | (k >> logT));
+      k2[j] = k1 == 0xffffffffu ? ((slab << 13) | 0x1fffu) | 0x80000000u : ((slab << 13) | ck);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < P; ++j) keys[tid + j * THREADS] = k2[j];
+    __syncthreads();
+  }
+  fps_bitonic_sort32<NP, THREADS>(keys, tid);
+
+  // ---- deal the points: slot = warp*32P + j*32 + lane
+  float px[P], py[P], pz[P], mind[P];
+  float slab_lo = 3.4e38f, slab_hi = -3.4e38f;
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int slot = warp * 32 * P + j * 32 + lane;
+    const unsigned kk = keys[slot];
+    const bool exists = (kk & 0x80000000u) == 0u;
+    const unsigned ck = kk & 0x1fffu;
+    const int k = !exists ? 0
+                  : (logT == 0 ? (int)ck
+                               : (int)((__brev(ck >> (13 - logT)) >> (32 - logT)) | ((ck & ((1u << (13 - logT)) - 1u)) << logT)));
+    sidx[slot] = k;
+    const float x = sx[k], y = sy[k], z = sz[k];
+    bool valid = exists;
+    if (exists) {
+      const float c = axis == 0 ? x : (axis == 1 ? y : z);
+      if (origin_skip) {
+        const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
+        valid = !((double)mag <= 1e-3);
+      }
+      if (valid) { slab_lo = fminf(slab_lo, c); slab_hi = fmaxf(slab_hi, c); }
+    }
+    px[j] = x; py[j] = y; pz[j] = z;
+    mind[j] = valid ? 1e10f : -1.0f;
+  }
+  for (int off = 16; off; off >>= 1) {
+    slab_lo = fminf(slab_lo, __shfl_xor_sync(PWCLO_FULL_MASK, slab_lo, off));
+    slab_hi = fmaxf(slab_hi, __shfl_xor_sync(PWCLO_FULL_MASK, slab_hi, off));
+  }
+  __syncthreads();
+
+  unsigned wv = 0u, wk = 0xffffffffu;   // cached warp (value, key)
+  float wmax = 1e10f;                   // cached largest running minimum of the warp (-1: no valid point)
+  int old = 0;
+  for (int r = 1; r < m; ++r) {
+    const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
+    const float qa = axis == 0 ? x1 : (axis == 1 ? y1 : z1);
+    const float dmin = fmaxf(fmaxf(__fsub_rn(slab_lo, qa), __fsub_rn(qa, slab_hi)), 0.f);
+    if (!(__fmul_rn(dmin, dmin) > wmax) && !(dbg && r > 1)) {     // warp-uniform: this slab may change
+      const int* my_idx = sidx + warp * 32 * P + lane;
+      // all P updates are independent; the arg-max is a log-depth tournament (earlier j wins ties, which
+      // is the reference's order because j ascends with the tie key) instead of a P-long select chain
+      float cv[P];
+      int cj[P];
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        const float d = dist2_ref_fma(px[j] - x1, py[j] - y1, pz[j] - z1);
+        const float d2 = fminf(d, mind[j]);
+        mind[j] = d2;
+        cv[j] = d2;
+        cj[j] = j;
+      }
+#pragma unroll
+      for (int w = 1; w < P; w <<= 1) {
+#pragma unroll
+        for (int j = 0; j + w < P; j += 2 * w) {
+          const bool take = cv[j + w] > cv[j];
+          cv[j] = take ? cv[j + w] : cv[j];
+          cj[j] = take ? cj[j + w] : cj[j];
+        }
+      }
+      const float best = cv[0] > -1.0f ? cv[0] : -1.0f;
+      const int bj = cv[0] > -1.0f ? cj[0] : 0;
+      const unsigned vb = best < 0.f ? 0u : __float_as_uint(best) + 1u;
+      wv = __reduce_max_sync(PWCLO_FULL_MASK, vb);
+      unsigned key = 0xffffffffu;
+      if (vb == wv) key = fps_key((unsigned)my_idx[bj * 32], logT);
+      wk = __reduce_min_sync(PWCLO_FULL_MASK, key);
+      wmax = wv == 0u ? -1.0f : __uint_as_float(wv - 1u);
+    }
+    const int buf = r & 1;
+    if (lane == 0) { red_val[buf][warp] = wv; red_key[buf][warp] = wk; }
+    __syncthreads();
+    const unsigned v2 = lane < NW ? red_val[buf][lane] : 0u;
+    const unsigned k2 = lane < NW ? red_key[buf][lane] : 0xffffffffu;
+    const unsigned bv = __reduce_max_sync(PWCLO_FULL_MASK, v2);
+    const unsigned bk = __reduce_min_sync(PWCLO_FULL_MASK, v2 == bv ? k2 : 0xffffffffu);
+    old = bv == 0u ? 0 : (int)fps_key_to_index(bk, logT);
+    if (tid == 0) idx[r] = old;
+  }
+}
+
+template <int P, int THREADS>
+static int launch_fps_slab(const float* xyz, int B, int n, int m, int logT, int origin_skip, int32_t* idx, cudaStream_t st) {
+  const size_t smem = (size_t)P * THREADS * (sizeof(unsigned) + sizeof(int)) + (size_t)3 * n * sizeof(float);
+  auto kern = fps_slab_kernel<P, THREADS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<B, THREADS, smem, st>>>(xyz, n, m, logT, origin_skip, idx, getenv("PWCLO_FPS_DBG_SKIPALL") ? 1 : 0);
+  return launch_status();
+}
+
 template <int P, int THREADS, int MODE>
 static int launch_fps(const float* xyz, int B, int n, int m, int logT, int origin_skip, float* scratch, int32_t* idx,
                       cudaStream_t st) {
@@ -161,6 +387,18 @@ PWCLO_API int pwclo_furthest_point_sampling(const float* xyz, int B, int N, int 
   while (T * 2 <= N && T * 2 <= cap) { T *= 2; ++logT; }
   const int skip = (flags & PWCLO_FPS_ORIGIN_SKIP) ? 1 : 0;
   // THREADS must be a multiple of T so that a thread's points share (k mod T): 512 or 1024 (cap 1024)
+  // slab-skipping kernel: worth its two in-kernel sorts once there are enough rounds and points
+  if (m >= 256 && N > 2048 && !getenv("PWCLO_FPS_NO_SLAB")) {
+    const bool wide = getenv("PWCLO_FPS_SLAB8") == nullptr;     // 512 threads x 16 points: fewer warps per barrier (7 % faster)
+    if (cap == 1024) {
+      if (N <= 4096) return launch_fps_slab<4, 1024>(xyz, B, N, m, logT, skip, idx, st);
+      if (N <= 8192) return launch_fps_slab<8, 1024>(xyz, B, N, m, logT, skip, idx, st);
+    } else {
+      if (N <= 4096) return launch_fps_slab<8, 512>(xyz, B, N, m, logT, skip, idx, st);
+      if (N <= 8192) return wide ? launch_fps_slab<16, 512>(xyz, B, N, m, logT, skip, idx, st)
+                                 : launch_fps_slab<8, 1024>(xyz, B, N, m, logT, skip, idx, st);
+    }
+  }
 #define FPS_CASE(P, TH, MODE) return launch_fps<P, TH, MODE>(xyz, B, N, m, logT, skip, nullptr, idx, st)
   if (cap == 1024 || N > 4096) {
     if (N <= 1024) FPS_CASE(1, 1024, 0);

@@ -120,6 +120,63 @@ __device__ __forceinline__ void geo16(float (&g)[16], const float* __restrict__ 
   for (int i = 10; i < 16; ++i) g[i] = 0.f;
 }
 
+// pooling over the neighbour axis (max for set conv, softmax-weighted sum for the cost volumes) of a
+// finished tile whose last activations sit in S0 (and S1), executed by all row threads
+template <int MODE>
+__device__ __forceinline__ void tc_pool(const TcArgs& a, const float* S0, const float* S1, int tid, int tile, int b,
+                                        int p0, int P) {
+  const int co = a.l[a.nlayers - 1].n;
+  if (MODE == TC_PW) {
+    const int co4 = co >> 2;
+    for (int e = tid; e < TC_ROWS * co4; e += TC_ROW_THREADS) {
+      const int rr = e / co4, c4 = e - rr * co4;
+      const int row = tile * TC_ROWS + rr;
+      if (row < a.S)
+        *reinterpret_cast<float4*>(a.out + (size_t)row * co + 4 * c4) =
+            *reinterpret_cast<const float4*>(S0 + (size_t)rr * a.ldS0 + 4 * c4);
+    }
+  } else if (MODE == TC_SA) {
+    for (int e = tid; e < P * co; e += TC_ROW_THREADS) {
+      const int p = e / co, c = e - p * co;
+      if (p0 + p >= a.S) continue;
+      const float* y = S0 + (size_t)(p * a.K) * a.ldS0 + c;
+      float m = y[0];
+      for (int k = 1; k < a.K; ++k) m = fmaxf(m, y[(size_t)k * a.ldS0]);
+      a.out[((size_t)b * a.S + p0 + p) * co + c] = m;
+    }
+  } else {
+    // two (point, channel) items per thread in flight: the per-item chain (LDS -> exp -> fma) is latency bound
+    const int items = P * 64;
+    for (int e0 = tid; e0 < items; e0 += 2 * TC_ROW_THREADS) {
+      const int e1 = e0 + TC_ROW_THREADS;
+      const bool has1 = e1 < items;
+      const int pA = e0 >> 6, cA = e0 & 63;
+      const int pB = has1 ? e1 >> 6 : pA, cB = has1 ? e1 & 63 : cA;
+      const float* attA = S0 + (size_t)(pA * a.K) * a.ldS0 + cA;
+      const float* valA = S1 + (size_t)(pA * a.K) * a.ldS1 + cA;
+      const float* attB = S0 + (size_t)(pB * a.K) * a.ldS0 + cB;
+      const float* valB = S1 + (size_t)(pB * a.K) * a.ldS1 + cB;
+      float mA = attA[0], mB = attB[0];
+#pragma unroll 4
+      for (int k = 1; k < a.K; ++k) {
+        mA = fmaxf(mA, attA[(size_t)k * a.ldS0]);
+        mB = fmaxf(mB, attB[(size_t)k * a.ldS0]);
+      }
+      float zA = 0.f, sA = 0.f, zB = 0.f, sB = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < a.K; ++k) {
+        const float exA = __expf(attA[(size_t)k * a.ldS0] - mA);   // 2 ulp: far inside the 1e-4 feature budget
+        const float exB = __expf(attB[(size_t)k * a.ldS0] - mB);
+        zA += exA; zB += exB;
+        sA = fmaf(exA, valA[(size_t)k * a.ldS1], sA);
+        sB = fmaf(exB, valB[(size_t)k * a.ldS1], sB);
+      }
+      if (p0 + pA < a.S) a.out[((size_t)b * a.S + p0 + pA) * 64 + cA] = __fdividef(sA, zA);
+      if (has1 && p0 + pB < a.S) a.out[((size_t)b * a.S + p0 + pB) * 64 + cB] = __fdividef(sB, zB);
+    }
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const TcArgs a, int ntiles, int tiles_per_cloud) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -223,6 +280,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const TcArgs a, i
     const int r = quad * 32 + lane;                // tile row == TMEM lane
     const uint32_t lane_base = tb + ((uint32_t)(quad * 32) << 16);
     uint32_t d_cnt = 0;
+    bool have_prev = false;
+    int prev_tile = 0, prev_b = 0, prev_p0 = 0, prev_P = TC_ROWS;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       // ---------------- gather the layer-0 input into the planes ----------------
       // 16-column groups are dealt round-robin to the 4 slices of a quadrant (group counter `grp`)
@@ -314,6 +373,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const TcArgs a, i
       tc_fence_before();
       mbar_arrive_a(aready_a);
       if (stamp) a.dbg[1] = clock64();
+      if (have_prev) {      // previous tile's pooling, overlapped with this tile's first GEMM
+        tc_pool<MODE>(a, S0, S1, tid, prev_tile, prev_b, prev_p0, prev_P);
+        have_prev = false;
+        rows_sync();        // S0 / S1 free before this tile's epilogues write them
+      }
 
       // ---------------- layer epilogues ----------------
       for (int L = 0; L < a.nlayers; ++L) {
@@ -350,46 +414,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const TcArgs a, i
       rows_sync();   // S0 / S1 complete
       if (stamp) a.dbg[20] = clock64();
 
-      // ---------------- pooling over the neighbour axis / output ----------------
-      const int co = a.l[a.nlayers - 1].n;
-      if (MODE == TC_PW) {
-        const int co4 = co >> 2;
-        for (int e = tid; e < TC_ROWS * co4; e += TC_ROW_THREADS) {
-          const int rr = e / co4, c4 = e - rr * co4;
-          const int row = tile * TC_ROWS + rr;
-          if (row < a.S)
-            *reinterpret_cast<float4*>(a.out + (size_t)row * co + 4 * c4) =
-                *reinterpret_cast<const float4*>(S0 + (size_t)rr * a.ldS0 + 4 * c4);
-        }
-      } else if (MODE == TC_SA) {
-        for (int e = tid; e < P * co; e += TC_ROW_THREADS) {
-          const int p = e / co, c = e - p * co;
-          if (p0 + p >= a.S) continue;
-          const float* y = S0 + (size_t)(p * a.K) * a.ldS0 + c;
-          float m = y[0];
-          for (int k = 1; k < a.K; ++k) m = fmaxf(m, y[(size_t)k * a.ldS0]);
-          a.out[((size_t)b * a.S + p0 + p) * co + c] = m;
-        }
+      // pooling of this tile is deferred: it runs after the NEXT tile's gather has been handed to the MMA
+      // warp, so it overlaps with that tile's first GEMM (cost volume 2 pools first: its gather writes S1)
+      if (MODE == TC_CV2) {
+        tc_pool<MODE>(a, S0, S1, tid, tile, b, p0, P);
+        rows_sync();
       } else {
-        for (int e = tid; e < P * 64; e += TC_ROW_THREADS) {
-          const int p = e >> 6, c = e & 63;
-          if (p0 + p >= a.S) continue;
-          const float* att = S0 + (size_t)(p * a.K) * a.ldS0 + c;
-          const float* val = S1 + (size_t)(p * a.K) * a.ldS1 + c;
-          float m = att[0];
-          for (int k = 1; k < a.K; ++k) m = fmaxf(m, att[(size_t)k * a.ldS0]);
-          float z = 0.f, s = 0.f;
-          for (int k = 0; k < a.K; ++k) {
-            const float ex = expf(att[(size_t)k * a.ldS0] - m);
-            z += ex;
-            s = fmaf(ex, val[(size_t)k * a.ldS1], s);
-          }
-          a.out[((size_t)b * a.S + p0 + p) * 64 + c] = s / z;
-        }
+        have_prev = true; prev_tile = tile; prev_b = b; prev_p0 = p0; prev_P = P;
       }
-      rows_sync();   // pooling done before the next tile's epilogues overwrite S0 / S1
       if (stamp) a.dbg[21] = clock64();
     }
+    if (have_prev) tc_pool<MODE>(a, S0, S1, tid, prev_tile, prev_b, prev_p0, prev_P);
   }
   tc_fence_before();
   __syncthreads();
