@@ -92,10 +92,11 @@ int pwclo_knn(const float *xyz, const float *new_xyz, int B, int N, int S, int K
 
 /* Same contract and bit-identical result as pwclo_knn, but exact search with sorted-slab pruning:
  * the reference points of every cloud are first sorted along their widest axis into `workspace`
- * (pwclo_knn_workspace_bytes(B,N) bytes, 16-byte aligned, caller-owned scratch), then each query scans
- * outwards from its own position only as far as its current K-th distance allows.  Falls back to
+ * (pwclo_knn_workspace_bytes(B,N,S) bytes, 16-byte aligned, caller-owned scratch) and the queries into
+ * Morton order; each query then scans outwards from its own position only as far as its current K-th
+ * distance (initially bounded through the previous, spatially adjacent query) allows.  Falls back to
  * the brute-force kernel when N > 8192 or the workspace is missing / too small. */
-size_t pwclo_knn_workspace_bytes(int B, int N);
+size_t pwclo_knn_workspace_bytes(int B, int N, int S);
 int pwclo_knn_sorted(const float *xyz, const float *new_xyz, int B, int N, int S, int K,
                      int sum_order, const float *warp_qt, float *warped_out, int32_t *idx,
                      float *dist, void *workspace, size_t workspace_bytes, void *stream);

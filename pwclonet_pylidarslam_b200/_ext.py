@@ -166,7 +166,7 @@ def knn(xyz, new_xyz, k, sum_order=None, warp_qt=None, return_warped=False, retu
         wq = _p(warp_qt) if warp_qt is not None else None
         wo = _p(warped) if warped is not None else None
         dp = _p(dist) if dist is not None else None
-        ws_bytes = L.pwclo_knn_workspace_bytes(B, N) if KNN_SORTED and N >= KNN_SORTED_MIN_N else 0
+        ws_bytes = L.pwclo_knn_workspace_bytes(B, N, S) if KNN_SORTED and N >= KNN_SORTED_MIN_N else 0
         if ws_bytes:
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device)
             _lib.check(L.pwclo_knn_sorted(_p(xyz), _p(new_xyz), B, N, S, int(k), so, wq, wo, _p(idx), dp, _p(ws), ws_bytes,

@@ -64,7 +64,7 @@ def lib():
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = ctypes.c_int
-        L.pwclo_knn_workspace_bytes.argtypes = [_i, _i]
+        L.pwclo_knn_workspace_bytes.argtypes = [_i, _i, _i]
         L.pwclo_knn_workspace_bytes.restype = ctypes.c_size_t
         L.pwclo_version.restype = ctypes.c_char_p
         L.pwclo_error_string.restype = ctypes.c_char_p

@@ -20,6 +20,8 @@
 //     refinement level never makes a round trip through HBM before its neighbour search.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pwclo {
@@ -271,7 +273,8 @@ __device__ __forceinline__ unsigned ordered_bits(float f) {
 __host__ __device__ inline size_t knn_ws_stride(int N) { return (size_t)4 * ((N + 3) & ~3) + 4; }  // floats per cloud
 
 __global__ void __launch_bounds__(SORT_THREADS)
-knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, float* __restrict__ ws) {
+knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, float* __restrict__ ws,
+                   const float* __restrict__ queries, int S, int SP, int* __restrict__ qorder) {
   extern __shared__ __align__(16) unsigned char sort_smem[];
   u64* keys = reinterpret_cast<u64*>(sort_smem);
   __shared__ float red[6][32];
@@ -334,6 +337,67 @@ knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, float* __restri
     reinterpret_cast<int*>(w)[3 * N4 + i] = id;
   }
   if (tid == 0) reinterpret_cast<int*>(w)[4 * N4] = axis;
+
+  // ---- query visiting order: Morton order (6 bits per axis) of the queries of this cloud, so that the
+  // queries a warp processes back to back are neighbours in space (their K-th distance + their mutual
+  // distance bounds the next query's K-th distance: a tight pruning bound from the first chunk on)
+  if (qorder == nullptr) return;
+  __syncthreads();
+  queries += (size_t)b * S * 3;
+  unsigned* qk = reinterpret_cast<unsigned*>(sort_smem);
+  float qmn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, qmx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+  for (int i = tid; i < S; i += SORT_THREADS)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float v = queries[i * 3 + d];
+      qmn[d] = fminf(qmn[d], v);
+      qmx[d] = fmaxf(qmx[d], v);
+    }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    for (int off = 16; off; off >>= 1) {
+      qmn[d] = fminf(qmn[d], __shfl_xor_sync(PWCLO_FULL_MASK, qmn[d], off));
+      qmx[d] = fmaxf(qmx[d], __shfl_xor_sync(PWCLO_FULL_MASK, qmx[d], off));
+    }
+    if (lane == 0) { red[d][warp] = qmn[d]; red[3 + d][warp] = qmx[d]; }
+  }
+  __syncthreads();
+  float lo3[3], sc3[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float a = CUDART_INF_F, c = -CUDART_INF_F;
+    for (int wv = 0; wv < SORT_THREADS / 32; ++wv) { a = fminf(a, red[d][wv]); c = fmaxf(c, red[3 + d][wv]); }
+    lo3[d] = a;
+    sc3[d] = c > a ? 63.999f / (c - a) : 0.f;
+  }
+  for (int i = tid; i < SP; i += SORT_THREADS) {
+    unsigned key = 0xffffffffu;
+    if (i < S) {
+      unsigned code = 0;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const unsigned cell = (unsigned)fminf(fmaxf((queries[i * 3 + d] - lo3[d]) * sc3[d], 0.f), 63.f);
+#pragma unroll
+        for (int bit = 0; bit < 6; ++bit) code |= ((cell >> bit) & 1u) << (3 * bit + d);
+      }
+      key = (code << 13) | (unsigned)i;
+    }
+    qk[i] = key;
+  }
+  __syncthreads();
+  for (int k = 2; k <= SP; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < SP / 2; t += SORT_THREADS) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int hi = lo | j;
+        const unsigned a = qk[lo], c = qk[hi];
+        const bool up = (lo & k) == 0;
+        if ((a > c) == up) { qk[lo] = c; qk[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < S; i += SORT_THREADS) qorder[(size_t)b * S + i] = (int)(qk[i] & 0x1fffu);
 }
 
 __device__ __forceinline__ void slab_mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -354,8 +418,8 @@ __device__ __forceinline__ void slab_mbar_wait(uint64_t* bar, uint32_t parity) {
 
 template <int SUM_ORDER>
 __global__ void __launch_bounds__(SLAB_WARPS * 32)
-knn_slab_kernel(const float* __restrict__ ws, const float* __restrict__ new_xyz, int N, int S, int K, int q_per_cta,
-                const float* __restrict__ warp_qt, float* __restrict__ warped_out, int32_t* __restrict__ idx_out,
+knn_slab_kernel(const float* __restrict__ ws, const int* __restrict__ qorder, const float* __restrict__ new_xyz, int N,
+                int S, int K, int q_per_cta, const float* __restrict__ warp_qt, float* __restrict__ warped_out, int32_t* __restrict__ idx_out,
                 float* __restrict__ dist_out) {
   extern __shared__ __align__(128) unsigned char slab_smem[];
   const int N4 = (N + 3) & ~3;
@@ -392,8 +456,13 @@ knn_slab_kernel(const float* __restrict__ ws, const float* __restrict__ new_xyz,
   const float* sa = axis == 0 ? sx : (axis == 1 ? sy : sz);
 
   const int flush_at = min(32, max(2 * K, 8));
-  const int q_end = min(S, (int)(blockIdx.x + 1) * q_per_cta);
-  for (int q = blockIdx.x * q_per_cta + warp; q < q_end; q += SLAB_WARPS) {
+  // each warp walks a contiguous run of the (Morton-ordered) query list of this CTA
+  const int c_begin = blockIdx.x * q_per_cta, c_end = min(S, c_begin + q_per_cta);
+  const int per_warp = (c_end - c_begin + SLAB_WARPS - 1) / SLAB_WARPS;
+  const int w_begin = c_begin + warp * per_warp, w_end = min(c_end, w_begin + per_warp);
+  float pqx = 0.f, pqy = 0.f, pqz = 0.f, prev_kth = CUDART_INF_F;   // previous query of this warp
+  for (int qpos = w_begin; qpos < w_end; ++qpos) {
+    const int q = qorder != nullptr ? qorder[(size_t)b * S + qpos] : qpos;
     float qx = new_xyz[q * 3 + 0], qy = new_xyz[q * 3 + 1], qz = new_xyz[q * 3 + 2];
     if (do_warp) {
       warp_point(pose, qx, qy, qz, qx, qy, qz);
@@ -402,6 +471,16 @@ knn_slab_kernel(const float* __restrict__ ws, const float* __restrict__ new_xyz,
         o[0] = qx; o[1] = qy; o[2] = qz;
       }
     }
+    // the K neighbours of the previous query lie within prev_kth + |q - q_prev| of this query, so this
+    // query's K-th distance cannot be larger (triangle inequality; rounded up, + 2e-5 relative slack)
+    float bound0 = CUDART_INF_F;
+    if (prev_kth < CUDART_INF_F) {
+      const float ex = qx - pqx, ey = qy - pqy, ez = qz - pqz;
+      const float dq = __fsqrt_ru(__fmaf_ru(ez, ez, __fmaf_ru(ey, ey, __fmul_ru(ex, ex))));
+      const float rr = __fadd_ru(prev_kth, dq);
+      bound0 = __fmul_ru(__fmul_ru(rr, rr), 1.00002f);
+    }
+    pqx = qx; pqy = qy; pqz = qz;
     const float qa = axis == 0 ? qx : (axis == 1 ? qy : qz);
     // first sorted position with sa[pos] >= qa
     int lo_b = 0, hi_b = N;
@@ -411,7 +490,7 @@ knn_slab_kernel(const float* __restrict__ ws, const float* __restrict__ new_xyz,
     }
     int left = lo_b - 1, right = lo_b;   // nearest unscanned positions on each side
     u64 list = KNN_INF_KEY;
-    float bound = CUDART_INF_F;
+    float bound = bound0;
     int cnt = 0;
     while (left >= 0 || right < N) {
       float el = CUDART_INF_F, er = CUDART_INF_F;   // squared axis distance of the nearest unscanned point
@@ -447,7 +526,7 @@ knn_slab_kernel(const float* __restrict__ ws, const float* __restrict__ new_xyz,
           if (lane < rest) { cand_d[lane] = md; cand_i[lane] = mi; }
           cnt = rest;
           list = knn_merge32(list, ck, lane);
-          bound = knn_bound(__uint_as_float((unsigned)(shfl_u64(list, K - 1) >> 32)));
+          bound = fminf(bound, knn_bound(__uint_as_float((unsigned)(shfl_u64(list, K - 1) >> 32))));
         }
       }
     }
@@ -457,6 +536,7 @@ knn_slab_kernel(const float* __restrict__ ws, const float* __restrict__ new_xyz,
       list = knn_merge32(list, ck, lane);
     }
     __syncwarp();
+    prev_kth = __uint_as_float((unsigned)(shfl_u64(list, K - 1) >> 32));
     if (lane < K) {
       const size_t o = ((size_t)b * S + q) * K + lane;
       idx_out[o] = (int)(unsigned)list;
@@ -467,9 +547,9 @@ knn_slab_kernel(const float* __restrict__ ws, const float* __restrict__ new_xyz,
 
 }  // namespace pwclo
 
-PWCLO_API size_t pwclo_knn_workspace_bytes(int B, int N) {
-  if (B <= 0 || N <= 0 || N > KNN_MAX_TILE) return 0;
-  return (size_t)B * knn_ws_stride(N) * sizeof(float);
+PWCLO_API size_t pwclo_knn_workspace_bytes(int B, int N, int S) {
+  if (B <= 0 || N <= 0 || S < 0 || N > KNN_MAX_TILE) return 0;
+  return (size_t)B * knn_ws_stride(N) * sizeof(float) + (size_t)B * S * sizeof(int);
 }
 
 PWCLO_API int pwclo_knn_sorted(const float* xyz, const float* new_xyz, int B, int N, int S, int K, int sum_order,
@@ -481,18 +561,23 @@ PWCLO_API int pwclo_knn_sorted(const float* xyz, const float* new_xyz, int B, in
   if (sum_order != PWCLO_KNN_SUM_XY_Z && sum_order != PWCLO_KNN_SUM_XZ_Y) return PWCLO_EINVAL;
   if (B == 0 || S == 0) return PWCLO_OK;
   if (B > 65535) return PWCLO_EUNSUPPORTED;
-  if (N > KNN_MAX_TILE || !workspace || workspace_bytes < pwclo_knn_workspace_bytes(B, N) || (uintptr_t)workspace % 16 != 0)
+  if (N > KNN_MAX_TILE || !workspace || workspace_bytes < pwclo_knn_workspace_bytes(B, N, S) || (uintptr_t)workspace % 16 != 0)
     return pwclo_knn(xyz, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist, stream);
   cudaStream_t st = (cudaStream_t)stream;
   int NP = 1;
   while (NP < N) NP <<= 1;
+  const int* qorder_used = nullptr;
   {
-    const size_t smem = (size_t)NP * sizeof(u64);
+    int SP = 1;
+    while (SP < S) SP <<= 1;
+    int* qorder = S <= 8192 && getenv("PWCLO_KNN_QORDER") ? reinterpret_cast<int*>((float*)workspace + (size_t)B * knn_ws_stride(N)) : nullptr;
+    const size_t smem = max((size_t)NP * sizeof(u64), qorder ? (size_t)SP * sizeof(unsigned) : (size_t)0);
     if (smem > 32 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(knn_presort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
-    knn_presort_kernel<<<B, SORT_THREADS, smem, st>>>(xyz, N, NP, (float*)workspace);
+    knn_presort_kernel<<<B, SORT_THREADS, smem, st>>>(xyz, N, NP, (float*)workspace, new_xyz, S, SP, qorder);
+    qorder_used = qorder;
     int rc = launch_status();
     if (rc) return rc;
   }
@@ -506,6 +591,6 @@ PWCLO_API int pwclo_knn_sorted(const float* xyz, const float* new_xyz, int B, in
     if (e != cudaSuccess) return (int)e;
   }
   dim3 grid(ceil_div(S, q_per_cta), B);
-  kern<<<grid, SLAB_WARPS * 32, smem, st>>>((const float*)workspace, new_xyz, N, S, K, q_per_cta, warp_qt, warped_out, idx, dist);
+  kern<<<grid, SLAB_WARPS * 32, smem, st>>>((const float*)workspace, qorder_used, new_xyz, N, S, K, q_per_cta, warp_qt, warped_out, idx, dist);
   return launch_status();
 }

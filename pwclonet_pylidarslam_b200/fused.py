@@ -226,7 +226,7 @@ class FusedPWCLONet:
         S = queries.shape[1]
         idx = self._new(B, S, k, dtype=torch.int32)
         warped = self._new(B, S, 3) if warp_qt is not None else None
-        ws_bytes = self.lib.pwclo_knn_workspace_bytes(B, N) if _ext.KNN_SORTED and N >= _ext.KNN_SORTED_MIN_N else 0
+        ws_bytes = self.lib.pwclo_knn_workspace_bytes(B, N, S) if _ext.KNN_SORTED and N >= _ext.KNN_SORTED_MIN_N else 0
         if ws_bytes:
             ws = self._new(ws_bytes, dtype=torch.uint8)
             self._call("pwclo_knn_sorted", _p(xyz), _p(queries), B, N, S, k, _ext.KNN_SUM_ORDER, _p(warp_qt), _p(warped),

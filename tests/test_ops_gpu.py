@@ -123,6 +123,17 @@ def test_knn_sorted_equals_bruteforce(cuda, B, N, S, K):
         assert torch.equal(d1, d0) and torch.equal(i1, i0)
 
 
+def test_knn_query_order_variant(cuda, monkeypatch):
+    """optional Morton query ordering + previous-query bound (PWCLO_KNN_QORDER=1): same bits"""
+    lid = np.stack([synthetic.make_pair(synthetic.SEED_BASE + 70 + i, 8192)["pc1"] for i in range(2)])
+    x = _dev(lid, cuda)
+    q = x[:, ::4].contiguous()
+    i0, d0 = _ext.knn(x, q, 16, return_dist=True)
+    monkeypatch.setenv("PWCLO_KNN_QORDER", "1")
+    i1, d1 = _ext.knn(x, q, 16, return_dist=True)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
+
+
 def _tie_aware_equal(got_i, ref_i, ref_d):
     """torch.topk leaves the order among equal distances unspecified: indices must agree wherever
     the reference distance is unique inside the row, and as sets inside groups of equal distance."""
