@@ -253,18 +253,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const TcArgs a, i
             const uint64_t dh0 = DESC_FIXED | (uint64_t)((slot & 0x3ffffu) >> 4);
             const uint64_t dl0 = DESC_FIXED | (uint64_t)(((slot + lo_off) & 0x3ffffu) >> 4);
             const int kn = min(4, ksteps - k0);
-            // A-operand column of the first k-step of this chunk; a chunk never straddles the two segments
-            // unless ks0 % 4 != 0, which the per-step select below handles
+            // full chunk inside one column segment (the common case): 12 MMAs from one asm block
+            const bool seg0 = k0 + 4 <= ks0, seg1 = k0 >= ks0;
+            if (kn == 4 && (seg0 || seg1)) {
+              const uint32_t col = (uint32_t)(seg0 ? col0 + 8 * k0 : col1 + 8 * (k0 - ks0));
+              tc_mma3x4_ts_warp(tb + COL_D, tb + COL_HI + col, tb + COL_LO + col, dh0, dl0, idesc, acc);
+              acc = 1;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (j < kn) {
-                const int ks = k0 + j;
-                const uint32_t col = (uint32_t)(ks < ks0 ? col0 + 8 * ks : col1 + 8 * (ks - ks0));
-                const uint64_t dh = dh0 + (uint64_t)(16 * j), dl = dl0 + (uint64_t)(16 * j);   // +256 B per k-step
-                tc_mma_ts_warp(tb + COL_D, tb + COL_HI + col, dh, idesc, acc);
-                tc_mma_ts_warp(tb + COL_D, tb + COL_LO + col, dh, idesc, 1);
-                tc_mma_ts_warp(tb + COL_D, tb + COL_HI + col, dl, idesc, 1);
-                acc = 1;
+              for (int j = 0; j < 4; ++j) {
+                if (j < kn) {
+                  const int ks = k0 + j;
+                  const uint32_t col = (uint32_t)(ks < ks0 ? col0 + 8 * ks : col1 + 8 * (ks - ks0));
+                  const uint64_t dh = dh0 + (uint64_t)(16 * j), dl = dl0 + (uint64_t)(16 * j);   // +256 B per k-step
+                  tc_mma3_ts_warp(tb + COL_D, tb + COL_HI + col, tb + COL_LO + col, dh, dl, idesc, acc);
+                  acc = 1;
+                }
               }
             }
             tc_commit_warp(empty_a + 8 * s);                    // slot reusable once these MMAs have read it

@@ -54,6 +54,51 @@ __device__ __forceinline__ void tc_mma_ts_warp(uint32_t d_tmem, uint32_t a_tmem,
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the three MMAs of one 3xTF32 k-step under a single election (fewer uniform-register moves / predicates)
+__device__ __forceinline__ void tc_mma3_ts_warp(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %3, %5, p;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %3, %5, 1;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %4, %5, 1;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_hi), "r"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// a whole 32-wide weight chunk: 4 k-steps x 3 MMAs, A columns advance by 8, descriptors by 256 B (+16)
+__device__ __forceinline__ void tc_mma3x4_ts_warp(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b32 ah1, ah2, ah3, al1, al2, al3;\n"
+      ".reg .b64 bh1, bh2, bh3, bl1, bl2, bl3;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "add.u32 ah1, %1, 8;  add.u32 ah2, %1, 16;  add.u32 ah3, %1, 24;\n"
+      "add.u32 al1, %2, 8;  add.u32 al2, %2, 16;  add.u32 al3, %2, 24;\n"
+      "add.u64 bh1, %3, 16; add.u64 bh2, %3, 32;  add.u64 bh3, %3, 48;\n"
+      "add.u64 bl1, %4, 16; add.u64 bl2, %4, 32;  add.u64 bl3, %4, 48;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %3, %5, p;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %3, %5, 1;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %4, %5, 1;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], bh1, %5, 1;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [al1], bh1, %5, 1;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], bl1, %5, 1;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], bh2, %5, 1;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [al2], bh2, %5, 1;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], bl2, %5, 1;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], bh3, %5, 1;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [al3], bh3, %5, 1;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], bl3, %5, 1;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_hi), "r"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_warp(uint32_t bar_addr) {
   asm volatile(
       "{\n"
