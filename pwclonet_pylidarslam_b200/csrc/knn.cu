@@ -545,6 +545,166 @@ knn_slab_kernel(const float* __restrict__ ws, const int* __restrict__ qorder, co
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Small-K variant of the slab search: G = 8 or 16 lanes per query, 32/G queries per warp in lock step.
+// The running list, the candidate queue and the bitonic sort/merge networks are G wide, so a merge
+// costs ~G/32 of the 32-lane version and four (two) queries share every instruction.  Same keys,
+// same pruning rule, same result bits.
+// -------------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ u64 knn_merge_g(u64 list, u64 cand, int gl) {
+#pragma unroll
+  for (int k = 2; k <= G; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const u64 other = shfl_xor_u64(cand, j);
+      const bool desc_block = (gl & k) == 0 || k == G;
+      const bool lower = (gl & j) == 0;
+      const bool keep_max = lower == desc_block;
+      cand = keep_max ? (cand > other ? cand : other) : (cand < other ? cand : other);
+    }
+  }
+  u64 c = list < cand ? list : cand;
+#pragma unroll
+  for (int j = G / 2; j > 0; j >>= 1) {
+    const u64 other = shfl_xor_u64(c, j);
+    const bool lower = (gl & j) == 0;
+    c = lower ? (c < other ? c : other) : (c > other ? c : other);
+  }
+  return c;
+}
+
+template <int SUM_ORDER, int G>
+__global__ void __launch_bounds__(SLAB_WARPS * 32)
+knn_slab_small_kernel(const float* __restrict__ ws, const float* __restrict__ new_xyz, int N, int S, int K, int q_per_cta,
+                      const float* __restrict__ warp_qt, float* __restrict__ warped_out, int32_t* __restrict__ idx_out,
+                      float* __restrict__ dist_out) {
+  constexpr int QPW = 32 / G;
+  extern __shared__ __align__(128) unsigned char slab_smem[];
+  const int N4 = (N + 3) & ~3;
+  float* sx = reinterpret_cast<float*>(slab_smem);
+  float* sy = sx + N4;
+  float* sz = sy + N4;
+  int* sid = reinterpret_cast<int*>(sz + N4);
+  int* hdr = sid + N4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / G, gl = lane % G;
+  const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (grp * G);
+  float* cand_d = reinterpret_cast<float*>(hdr + 4) + (size_t)warp * KNN_BUF + grp * 2 * G;
+  int* cand_i = reinterpret_cast<int*>(reinterpret_cast<float*>(hdr + 4) + (size_t)SLAB_WARPS * KNN_BUF) + (size_t)warp * KNN_BUF + grp * 2 * G;
+  __shared__ __align__(8) uint64_t bar;
+
+  const int b = blockIdx.y;
+  const float* w = ws + (size_t)b * knn_ws_stride(N);
+  if (threadIdx.x == 0) {
+    const uint32_t baddr = (uint32_t)__cvta_generic_to_shared(&bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(baddr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)(knn_ws_stride(N) * sizeof(float));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(baddr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(sx)),
+                 "l"(w), "r"(bytes), "r"(baddr)
+                 : "memory");
+  }
+  __syncthreads();
+  new_xyz += (size_t)b * S * 3;
+  PoseQT pose;
+  const bool do_warp = warp_qt != nullptr;
+  if (do_warp) pose = make_pose(warp_qt + (size_t)b * 7);
+  slab_mbar_wait(&bar, 0);
+  const int axis = hdr[0];
+  const float* sa = axis == 0 ? sx : (axis == 1 ? sy : sz);
+  int nsearch = 1;                       // binary-search steps: enough for N + 1 outcomes
+  while ((1 << nsearch) < N + 1) ++nsearch;
+
+  const int flush_at = min(G, max(2 * K, 8));
+  const int c_begin = blockIdx.x * q_per_cta, c_end = min(S, c_begin + q_per_cta);
+  for (int q0 = c_begin + warp * QPW; q0 < c_end; q0 += SLAB_WARPS * QPW) {
+    const int q = q0 + grp;
+    const bool has_q = q < c_end;
+    const int qq = has_q ? q : c_end - 1;
+    float qx = new_xyz[qq * 3 + 0], qy = new_xyz[qq * 3 + 1], qz = new_xyz[qq * 3 + 2];
+    if (do_warp) {
+      warp_point(pose, qx, qy, qz, qx, qy, qz);
+      if (warped_out != nullptr && gl == 0 && has_q) {
+        float* o = warped_out + ((size_t)b * S + q) * 3;
+        o[0] = qx; o[1] = qy; o[2] = qz;
+      }
+    }
+    const float qa = axis == 0 ? qx : (axis == 1 ? qy : qz);
+    int lo_b = 0, hi_b = N;              // first sorted position with sa[pos] >= qa (fixed trip count: no divergence)
+    for (int it = 0; it < nsearch; ++it) {
+      const int mid = (lo_b + hi_b) >> 1;
+      const bool go = lo_b < hi_b && sa[min(mid, N - 1)] < qa;
+      const bool stay = lo_b < hi_b && !go;
+      lo_b = go ? mid + 1 : lo_b;
+      hi_b = stay ? mid : hi_b;
+    }
+    int left = lo_b - 1, right = lo_b;
+    u64 list = KNN_INF_KEY;
+    float bound = CUDART_INF_F;
+    int cnt = 0;
+    while (true) {
+      float el = CUDART_INF_F, er = CUDART_INF_F;
+      if (left >= 0) { const float d = __fsub_rn(qa, sa[left]); el = __fmul_rn(d, d); }
+      if (right < N) { const float d = __fsub_rn(qa, sa[right]); er = __fmul_rn(d, d); }
+      const bool go_left = el <= er;
+      const float e = go_left ? el : er;
+      const bool active = has_q && (left >= 0 || right < N) && e <= bound;   // uniform within a group
+      if (!__any_sync(PWCLO_FULL_MASK, active)) break;
+      int pos = 0;
+      if (active) {
+        if (go_left) { pos = left - gl; left -= G; }
+        else { pos = right + gl; right += G; }
+      }
+      const bool rv = active && pos >= 0 && pos < N;
+      const int pc = rv ? pos : 0;
+      const float dx = __fsub_rn(qx, sx[pc]), dy = __fsub_rn(qy, sy[pc]), dz = __fsub_rn(qz, sz[pc]);
+      const float xx = __fmul_rn(dx, dx), yy = __fmul_rn(dy, dy), zz = __fmul_rn(dz, dz);
+      const float d2 = SUM_ORDER == 0 ? __fadd_rn(__fadd_rn(xx, yy), zz) : __fadd_rn(__fadd_rn(xx, zz), yy);
+      const bool pass = rv && d2 <= bound;
+      const unsigned mask = __ballot_sync(PWCLO_FULL_MASK, pass);
+      if (mask) {   // warp-uniform
+        const unsigned gm = mask & gmask;
+        if (pass) {
+          const int slot = cnt + __popc(gm & ((1u << lane) - 1u));
+          cand_d[slot] = d2;
+          cand_i[slot] = sid[pc];
+        }
+        cnt += __popc(gm);
+        const bool flush = cnt >= flush_at;
+        if (__any_sync(PWCLO_FULL_MASK, flush)) {
+          __syncwarp();
+          const u64 ck = flush && gl < cnt ? knn_key(__fsqrt_rn(__fadd_rn(cand_d[gl], 1e-8f)), cand_i[gl]) : KNN_INF_KEY;
+          const int rest = flush ? max(cnt - G, 0) : 0;
+          float md = 0.f; int mi = 0;
+          if (gl < rest) { md = cand_d[G + gl]; mi = cand_i[G + gl]; }
+          __syncwarp();
+          if (gl < rest) { cand_d[gl] = md; cand_i[gl] = mi; }
+          if (flush) cnt = rest;
+          list = knn_merge_g<G>(list, ck, gl);      // groups that do not flush merge an all-INF batch: a no-op
+          // (shuffle executed by every lane: `flush` differs between the groups of a warp)
+          const unsigned kv = (unsigned)(__shfl_sync(PWCLO_FULL_MASK, (unsigned)(list >> 32), K - 1, G));
+          if (flush) bound = fminf(bound, knn_bound(__uint_as_float(kv)));
+        }
+      }
+    }
+    __syncwarp();
+    {
+      const u64 ck = gl < cnt ? knn_key(__fsqrt_rn(__fadd_rn(cand_d[gl], 1e-8f)), cand_i[gl]) : KNN_INF_KEY;
+      list = knn_merge_g<G>(list, ck, gl);
+    }
+    __syncwarp();
+    if (has_q && gl < K) {
+      const size_t o = ((size_t)b * S + q) * K + gl;
+      idx_out[o] = (int)(unsigned)list;
+      if (dist_out) dist_out[o] = __uint_as_float((unsigned)(list >> 32));
+    }
+  }
+}
+
 }  // namespace pwclo
 
 PWCLO_API size_t pwclo_knn_workspace_bytes(int B, int N, int S) {
@@ -585,12 +745,23 @@ PWCLO_API int pwclo_knn_sorted(const float* xyz, const float* new_xyz, int B, in
   // queries per CTA: amortise the shared-memory fill, keep >= ~3 CTAs per SM in flight overall
   int q_per_cta = SLAB_WARPS;
   while (q_per_cta * 2 <= S && (long long)B * ceil_div(S, q_per_cta * 2) >= 3LL * kNumSM) q_per_cta *= 2;
+  dim3 grid(ceil_div(S, q_per_cta), B);
+  if (K <= 16 && N >= 16 && !getenv("PWCLO_KNN_NO_SMALL")) {   // G lanes per query, 32/G queries per warp
+    void (*ks)(const float*, const float*, int, int, int, int, const float*, float*, int32_t*, float*);
+    if (K <= 8) ks = sum_order == PWCLO_KNN_SUM_XY_Z ? knn_slab_small_kernel<0, 8> : knn_slab_small_kernel<1, 8>;
+    else ks = sum_order == PWCLO_KNN_SUM_XY_Z ? knn_slab_small_kernel<0, 16> : knn_slab_small_kernel<1, 16>;
+    if (smem > 32 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    ks<<<grid, SLAB_WARPS * 32, smem, st>>>((const float*)workspace, new_xyz, N, S, K, q_per_cta, warp_qt, warped_out, idx, dist);
+    return launch_status();
+  }
   auto kern = sum_order == PWCLO_KNN_SUM_XY_Z ? knn_slab_kernel<0> : knn_slab_kernel<1>;
   if (smem > 32 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  dim3 grid(ceil_div(S, q_per_cta), B);
   kern<<<grid, SLAB_WARPS * 32, smem, st>>>((const float*)workspace, qorder_used, new_xyz, N, S, K, q_per_cta, warp_qt, warped_out, idx, dist);
   return launch_status();
 }
