@@ -155,12 +155,15 @@ int pwclo_pose_head(const float *emb, const float *mask, int B, int S, const flo
                     const float *bt, const float *coarse_qt, float *qt_out, float *pose_params,
                     int level, void *stream);
 
-/* Tensor-core versions (tcgen05.mma kind::tf32, error-compensated 3xTF32, activations resident in
- * TMEM) of the four layer kernels above; same arguments and results (fp32-class accuracy), but
- * pwclo_layer_t.w is packed for the tensor cores: [ceil(K/32)][hi,lo][cout/8][8][8][4] fp32 with
- * w_hi = w & 0xffffe000, w_lo = w - w_hi, element (n, k) of a chunk at ((n/8)*8 + (k%32)/4)*32 + (n%8)*4 + k%4
- * (canonical K-major no-swizzle UMMA layout; reference packer: pwclonet_pylidarslam_b200/tc_pack.py).
- * cout must be 64 or 128.  Input-channel orders: set_conv (features(C), xyz_diff(3), 0 x5);
+/* Tensor-core versions (tcgen05.mma, activations resident in TMEM) of the four layer kernels above;
+ * same arguments and results (fp32-class accuracy: D += tf32(A)*tf32(W) + bf16(A-tf32(A))*bf16(W) +
+ * bf16(A)*bf16(W-tf32(W)), kind::tf32 + 2 x kind::f16 MMAs, relative error ~1e-6).
+ * pwclo_layer_t.w is packed for the tensor cores, per chunk of 32 input channels (cout*256 bytes):
+ *   [tf32_rna(W)          fp32, element (n,k) at float ((n/8)*8 + k/4)*32 + (n%8)*4 + k%4 ]  cout*128 B
+ *   [bf16_rn(W)           bf16, element (n,k) at half  ((n/8)*4 + k/8)*64 + (n%8)*8 + k%8 ]  cout*64 B
+ *   [bf16_rn(W - tf32(W)) bf16, same layout]                                                cout*64 B
+ * (canonical K-major no-swizzle UMMA layouts; reference packer: pwclonet_pylidarslam_b200/tc_pack.py
+ * pack_tc2).  cout must be 64 or 128.  Input-channel orders: set_conv (features(C), xyz_diff(3), 0 x13);
  * cost_volume_1 mlp1[0] (f1(C), f2(C), geo(10), 0 x6), enc (geo(10), 0 x6); cost_volume_2 as above. */
 int pwclo_set_conv_tc(const float *xyz, const float *feats, const float *new_xyz, const int32_t *idx,
                       int B, int N, int S, int K, int C, const pwclo_layer_t *layers, int nlayers,
@@ -176,7 +179,8 @@ int pwclo_cost_volume_2_tc(const float *wxyz, const float *f1, const float *e1, 
                            const pwclo_layer_t *mlp3, float *out, void *stream);
 
 /* Diagnostic: D[128,N] = A[128,K] * W[N,K]^T on the tcgen05 tensor cores (A split hi/lo in TMEM, W packed
- * hi/lo in the canonical K-major chunks, see csrc/tc_mma.cuh).  mode 1 = plain TF32, 3 = 3xTF32. */
+ * hi/lo in the canonical K-major chunks, see csrc/tc_mma.cuh).  mode 1 = plain TF32, 3 = 3xTF32 (wpk from
+ * tc_pack.pack_tc), 5 = tf32 + bf16 correction terms (wpk from tc_pack.pack_tc2, the layout above). */
 int pwclo_tc_selftest(const float *A, const float *wpk, int K, int N, int mode, float *D, void *stream);
 
 /* out[b,j,:] = xyz[b,idx[b,j],:]  (gather_operation on [B,N,3], P2/pointnet2_modules.py:200-206) */

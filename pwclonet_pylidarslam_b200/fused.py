@@ -135,7 +135,7 @@ class FusedPWCLONet:
                             if src >= 0:
                                 Wi[:, dst] = Wn[:, src]
                         Wn = Wi
-                    tcr.append({"w_off": A.add(tc_pack.pack_tc(Wn)), "b_off": A.add(b.float().numpy()),
+                    tcr.append({"w_off": A.add(tc_pack.pack_tc2(Wn)), "b_off": A.add(b.float().numpy()),
                                 "cin": W.shape[1], "cout": W.shape[0]})
             self.recs[prefix] = recs
             if len(tcr) == len(recs):
@@ -146,7 +146,7 @@ class FusedPWCLONet:
 
         for name in ("psa_1", "psa_2", "psa_3", "psa_4", "flow_feature_encoding"):
             cin = sd[f"{name}.mlp_module.layer0.conv.weight"].shape[1]
-            mlp(f"{name}.mlp_module", sa_order(cin), tc_first_order=sa_order(cin) + [-1] * 5)
+            mlp(f"{name}.mlp_module", sa_order(cin), tc_first_order=sa_order(cin) + [-1] * 13)
 
         def cost_volume(prefix):
             cin = sd[f"{prefix}.mlp_convs.layer0.conv.weight"].shape[1]
@@ -173,7 +173,7 @@ class FusedPWCLONet:
             p = f"pose_warp_refinement_{l}"
             for up in ("setupconv_features", "setupconv_mask"):
                 cin_up = sd[f"{p}.{up}.mlp.layer0.conv.weight"].shape[1]
-                mlp(f"{p}.{up}.mlp", tc_first_order=list(range(cin_up)) + [-1] * 5)   # (features, xyz_diff) + pad
+                mlp(f"{p}.{up}.mlp", tc_first_order=list(range(cin_up)) + [-1] * 13)   # (features, xyz_diff) + pad to 16
                 mlp(f"{p}.{up}.post_mlp")
             cost_volume(f"{p}.cost_volume")
             mlp(f"{p}.flow_predictor_features.mlp_convs")

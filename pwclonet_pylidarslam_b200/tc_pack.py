@@ -30,3 +30,39 @@ def pack_tc(W):
         v = m.reshape(N // 8, 8, K32 // 32, 8, 4)          # [n/8, n%8, chunk, kc, k%4]
         out[:, part] = v.transpose(2, 0, 3, 1, 4)
     return out.reshape(-1)
+
+
+def tf32_rna(w):
+    """round-to-nearest (ties away) to 10 explicit mantissa bits, like cvt.rna.tf32.f32"""
+    u = np.ascontiguousarray(w, np.float32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
+
+
+def bf16_bits(w):
+    """round-to-nearest-even bfloat16 bit patterns (uint16) of an fp32 array"""
+    u = np.ascontiguousarray(w, np.float32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+
+
+def pack_tc2(W):
+    """Hybrid packing (tc_mma.cuh v2): per 32-input chunk
+         [tf32(W)        fp32  [N/8][k/4 (8)][n%8][k%4]]   N*128 B
+         [bf16(W)        bf16  [N/8][k/8 (4)][n%8][k%8]]   N*64 B
+         [bf16(W-tf32(W)) bf16 same layout]                N*64 B
+    returned as a flat fp32 view (N*64 floats per chunk)."""
+    W = np.asarray(W, np.float64)
+    N, K = W.shape
+    assert N % 8 == 0
+    K32 = (K + 31) // 32 * 32
+    Wp = np.zeros((N, K32), np.float32)
+    Wp[:, :K] = W.astype(np.float32)
+    hi = tf32_rna(Wp)
+    lo = (Wp - hi).astype(np.float32)
+    nch = K32 // 32
+    out = np.empty((nch, N * 256), np.uint8)
+    t = hi.reshape(N // 8, 8, nch, 8, 4).transpose(2, 0, 3, 1, 4)            # [chunk, n/8, k/4, n%8, k%4]
+    out[:, : N * 128] = np.ascontiguousarray(t).reshape(nch, -1).view(np.uint8)
+    for j, m in enumerate((bf16_bits(Wp), bf16_bits(lo))):
+        v = m.reshape(N // 8, 8, nch, 4, 8).transpose(2, 0, 3, 1, 4)         # [chunk, n/8, k/8, n%8, k%8]
+        out[:, N * 128 + j * N * 64: N * 128 + (j + 1) * N * 64] = np.ascontiguousarray(v).reshape(nch, -1).view(np.uint8)
+    return out.reshape(-1).view(np.float32)
