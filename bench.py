@@ -286,7 +286,8 @@ def main():
                 return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
                         "frac": ach / tf_peak, "traffic": None, "peak_kind": peak_kind + " (cuBLAS bf16 sustained)",
                         "ms_per_step": ms, "launches_per_step": len(per_kernel[name]),
-                        "note": "fp32-accurate 3xTF32: 3 tensor-core MMAs per product; flops counted once"}
+                        "note": "fp32-accurate split product (tf32 + 2 bf16 correction MMAs: 8 tcgen05.mma per 32 inputs); "
+                                "flops counted once; the kernels are bound by TMEM operand/accumulator reads, see DESIGN.md"}
             ach = by / (ms * 1e-3) / 1e9
             return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                     "traffic": None, "peak_kind": peak_kind, "ms_per_step": ms, "launches_per_step": len(per_kernel[name]),

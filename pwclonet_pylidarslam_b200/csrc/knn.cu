@@ -417,7 +417,7 @@ __device__ __forceinline__ void slab_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 template <int SUM_ORDER>
-__global__ void __launch_bounds__(SLAB_WARPS * 32)
+__global__ void __launch_bounds__(1024)
 knn_slab_kernel(const float* __restrict__ ws, const int* __restrict__ qorder, const float* __restrict__ new_xyz, int N,
                 int S, int K, int q_per_cta, const float* __restrict__ warp_qt, float* __restrict__ warped_out, int32_t* __restrict__ idx_out,
                 float* __restrict__ dist_out) {
@@ -428,9 +428,9 @@ knn_slab_kernel(const float* __restrict__ ws, const int* __restrict__ qorder, co
   float* sz = sy + N4;
   int* sid = reinterpret_cast<int*>(sz + N4);
   int* hdr = sid + N4;                        // [0] = axis
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   float* cand_d = reinterpret_cast<float*>(hdr + 4) + (size_t)warp * KNN_BUF;
-  int* cand_i = reinterpret_cast<int*>(reinterpret_cast<float*>(hdr + 4) + (size_t)SLAB_WARPS * KNN_BUF) + (size_t)warp * KNN_BUF;
+  int* cand_i = reinterpret_cast<int*>(reinterpret_cast<float*>(hdr + 4) + (size_t)nwarps * KNN_BUF) + (size_t)warp * KNN_BUF;
   __shared__ __align__(8) uint64_t bar;
 
   const int b = blockIdx.y;
@@ -458,7 +458,7 @@ knn_slab_kernel(const float* __restrict__ ws, const int* __restrict__ qorder, co
   const int flush_at = min(32, max(2 * K, 8));
   // each warp walks a contiguous run of the (Morton-ordered) query list of this CTA
   const int c_begin = blockIdx.x * q_per_cta, c_end = min(S, c_begin + q_per_cta);
-  const int per_warp = (c_end - c_begin + SLAB_WARPS - 1) / SLAB_WARPS;
+  const int per_warp = (c_end - c_begin + nwarps - 1) / nwarps;
   const int w_begin = c_begin + warp * per_warp, w_end = min(c_end, w_begin + per_warp);
   float pqx = 0.f, pqy = 0.f, pqz = 0.f, prev_kth = CUDART_INF_F;   // previous query of this warp
   for (int qpos = w_begin; qpos < w_end; ++qpos) {
@@ -758,10 +758,18 @@ PWCLO_API int pwclo_knn_sorted(const float* xyz, const float* new_xyz, int B, in
     return launch_status();
   }
   auto kern = sum_order == PWCLO_KNN_SUM_XY_Z ? knn_slab_kernel<0> : knn_slab_kernel<1>;
-  if (smem > 32 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // a cloud that leaves room for only one CTA per SM gets 32 warps per CTA (the search is latency bound)
+  const int warps = smem > 100 * 1024 && !getenv("PWCLO_KNN_16W") ? 32 : SLAB_WARPS;
+  const size_t smem_k = knn_ws_stride(N) * sizeof(float) + (size_t)warps * KNN_BUF * 8 + 128;
+  if (warps != SLAB_WARPS) {
+    q_per_cta = warps;
+    while (q_per_cta * 2 <= S && (long long)B * ceil_div(S, q_per_cta * 2) >= 3LL * kNumSM) q_per_cta *= 2;
+    grid = dim3(ceil_div(S, q_per_cta), B);
+  }
+  if (smem_k > 32 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k);
     if (e != cudaSuccess) return (int)e;
   }
-  kern<<<grid, SLAB_WARPS * 32, smem, st>>>((const float*)workspace, qorder_used, new_xyz, N, S, K, q_per_cta, warp_qt, warped_out, idx, dist);
+  kern<<<grid, warps * 32, smem_k, st>>>((const float*)workspace, qorder_used, new_xyz, N, S, K, q_per_cta, warp_qt, warped_out, idx, dist);
   return launch_status();
 }

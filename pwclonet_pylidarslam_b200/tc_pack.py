@@ -1,4 +1,5 @@
-"""Host-side packing of folded weights for the tcgen05 (3xTF32) layer kernels.
+"""Host-side packing of folded weights for the tcgen05 layer kernels (pack_tc2: the hybrid tf32 + bf16
+scheme the kernels use; pack_tc: the plain hi/lo 3xTF32 layout kept for the self-test).
 
 A weight matrix W [N, K] (N outputs, K inputs, K-major like a torch conv weight) is split into
 tf32-exact hi / lo parts and stored chunk-wise in the canonical K-major no-swizzle shared-memory
