@@ -246,19 +246,24 @@ PWCLO_API int pwclo_knn(const float* xyz, const float* new_xyz, int B, int N, in
 }
 
 // =================================================================================================
-// Sorted-slab exact kNN (the default path for N <= 8192 when the caller provides a workspace).
+// Sorted-strip exact kNN (the default path for N <= 8192 when the caller provides a workspace).
 //
 // Brute force evaluates S*N pairs; for LiDAR clouds the K-th neighbour is ~0.5 m away while the
 // cloud spans ~60 m, so almost all of that work is provably useless.  Two kernels:
 //   1. knn_presort_kernel: one CTA per cloud sorts the reference points along the axis of largest
-//      extent (64-bit (ordered coordinate, index) keys, bitonic sort in shared memory) and writes
-//      the sorted SoA (x, y, z, original index) + the axis id to the workspace.
-//   2. knn_slab_kernel: the sorted cloud is staged in shared memory by ONE TMA bulk copy; a warp
-//      binary-searches its query's position and scans 32-point chunks outwards on both sides,
-//      nearest side first, until the squared axis distance of the next unscanned point exceeds the
-//      conservative bound of the current K-th neighbour.  Distances, keys, queueing and merging are
-//      exactly those of the brute-force kernel, so the result is bit-identical: a skipped point has
-//      d2 >= dx2 > bound, hence sqrt(d2+1e-8) > K-th distance (strictly).
+//      extent a1 (64-bit (ordered coordinate, index) keys, bitonic sort in shared memory), cuts the
+//      sorted sequence into T equal-count strips and sorts every strip along the axis of second
+//      largest extent a2.  It writes the strip-major SoA (x, y, z, original index), the axis ids and
+//      the a1 boundaries of the strips to the workspace.
+//   2. knn_slab_kernel / knn_slab_small_kernel: the sorted cloud is staged in shared memory by ONE
+//      TMA bulk copy; a warp (or an 8/16-lane group) visits the strips nearest-first along a1 and,
+//      inside a strip, binary-searches its query's a2 position and scans chunks outwards on both
+//      sides, nearest side first, until  rd(e1 + e2) > bound, where e1 / e2 are the squared a1
+//      distance to the strip and the squared a2 distance to the next unscanned point, and bound is
+//      the conservative bound of the current K-th neighbour.  Distances, keys, queueing and merging
+//      are exactly those of the brute-force kernel, so the result is bit-identical: the computed
+//      d2 = fl(fl(A + B) + C) of a skipped point is >= rd(e1 + e2) > bound (fp32 addition of
+//      non-negative terms and subtraction are monotone), hence sqrt(d2+1e-8) > K-th distance.
 // =================================================================================================
 namespace pwclo {
 
@@ -270,15 +275,27 @@ __device__ __forceinline__ unsigned ordered_bits(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-__host__ __device__ inline size_t knn_ws_stride(int N) { return (size_t)4 * ((N + 3) & ~3) + 4; }  // floats per cloud
+constexpr int KNN_MAX_STRIPS = 32;
+// floats per cloud: x | y | z | id (N4 each) | hdr (axis1, axis2, strips, log2 strip length) | strip bounds (KNN_MAX_STRIPS + 4)
+__host__ __device__ inline size_t knn_ws_stride(int N) { return (size_t)4 * ((N + 3) & ~3) + 4 + KNN_MAX_STRIPS + 4; }
+// strips for a cloud padded to NP (power of two) points
+__host__ __device__ inline int knn_log_strip(int NP, int K, int strips_req) {
+  // measured on B200 (tools/run_knn.py): 16 strips for the big clouds, 8 when 32 neighbours are wanted from 2048 points
+  int T = strips_req > 0 ? strips_req : (NP >= 4096 || (NP >= 2048 && K <= 16) ? 16 : (NP >= 512 ? 8 : (NP >= 128 ? 4 : 1)));
+  if (T > KNN_MAX_STRIPS) T = KNN_MAX_STRIPS;
+  int logL = 0;
+  while ((1 << logL) < NP) ++logL;
+  while (T > 1 && logL > 5) { T >>= 1; --logL; }   // strip length >= 32 points
+  return logL;
+}
 
 __global__ void __launch_bounds__(SORT_THREADS)
-knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, float* __restrict__ ws,
+knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, int logL, float* __restrict__ ws,
                    const float* __restrict__ queries, int S, int SP, int* __restrict__ qorder) {
   extern __shared__ __align__(16) unsigned char sort_smem[];
   u64* keys = reinterpret_cast<u64*>(sort_smem);
   __shared__ float red[6][32];
-  __shared__ int axis_s;
+  __shared__ int axis_s, axis2_s;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   xyz += (size_t)b * N * 3;
   float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
@@ -305,10 +322,16 @@ knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, float* __restri
       for (int w = 0; w < SORT_THREADS / 32; ++w) { a = fminf(a, red[d][w]); c = fmaxf(c, red[3 + d][w]); }
       ext[d] = c - a;
     }
-    axis_s = (ext[0] >= ext[1] && ext[0] >= ext[2]) ? 0 : (ext[2] >= ext[1] ? 2 : 1);
+    const int a1 = (ext[0] >= ext[1] && ext[0] >= ext[2]) ? 0 : (ext[2] >= ext[1] ? 2 : 1);
+    const int o1 = (a1 + 1) % 3, o2 = (a1 + 2) % 3;
+    const int a2 = ext[o1] >= ext[o2] ? o1 : o2;
+    // a single strip is a plain slab search: it should run along the longest axis
+    const bool one = (1 << logL) >= NP;
+    axis_s = one ? a2 : a1;
+    axis2_s = one ? a1 : a2;
   }
   __syncthreads();
-  const int axis = axis_s;
+  const int axis = axis_s, axis2 = axis2_s;
   for (int i = tid; i < NP; i += SORT_THREADS)
     keys[i] = i < N ? (((u64)ordered_bits(xyz[i * 3 + axis]) << 32) | (unsigned)i) : ~0ull;
   __syncthreads();
@@ -326,17 +349,51 @@ knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, float* __restri
   }
   const int N4 = (N + 3) & ~3;
   float* w = ws + (size_t)b * knn_ws_stride(N);
+  // ---- strips: equal-count cuts of the a1 order; bounds[t] = a1 of the first point of strip t,
+  //      bounds[strips] = a1 of the last point
+  const int L = 1 << logL;
+  const int strips = (N + L - 1) >> logL;
+  if (tid <= strips) {
+    const int rnk = min(tid << logL, N - 1);
+    w[4 * N4 + 4 + tid] = xyz[(int)(unsigned)keys[rnk] * 3 + axis];
+  }
+  if (tid == 0) {
+    int* h = reinterpret_cast<int*>(w) + 4 * N4;
+    h[0] = axis; h[1] = axis2; h[2] = strips; h[3] = logL;
+  }
+  __syncthreads();   // bounds read before the keys are rewritten
+  // ---- every strip sorted along a2: key = (strip, ordered a2, index)
+  for (int i = tid; i < NP; i += SORT_THREADS) {
+    u64 k2 = ~0ull;
+    if (i < N) {
+      const unsigned id = (unsigned)keys[i];
+      k2 = ((u64)(i >> logL) << 45) | ((u64)ordered_bits(xyz[id * 3 + axis2]) << 13) | id;
+    }
+    keys[i] = k2;
+  }
+  __syncthreads();
+  for (int k = 2; k <= L; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < NP / 2; t += SORT_THREADS) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int hi = lo | j;
+        const u64 a = keys[lo], c = keys[hi];
+        const bool up = k == L || (lo & k) == 0;      // last stage: every strip ascending
+        if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
   for (int i = tid; i < N4; i += SORT_THREADS) {
     float x = CUDART_INF_F, y = CUDART_INF_F, z = CUDART_INF_F;
     int id = 0;
     if (i < N) {
-      id = (int)(unsigned)keys[i];
+      id = (int)((unsigned)keys[i] & 0x1fffu);
       x = xyz[id * 3 + 0]; y = xyz[id * 3 + 1]; z = xyz[id * 3 + 2];
     }
     w[i] = x; w[N4 + i] = y; w[2 * N4 + i] = z;
     reinterpret_cast<int*>(w)[3 * N4 + i] = id;
   }
-  if (tid == 0) reinterpret_cast<int*>(w)[4 * N4] = axis;
 
   // ---- query visiting order: Morton order (6 bits per axis) of the queries of this cloud, so that the
   // queries a warp processes back to back are neighbours in space (their K-th distance + their mutual
@@ -429,8 +486,8 @@ knn_slab_kernel(const float* __restrict__ ws, const int* __restrict__ qorder, co
   int* sid = reinterpret_cast<int*>(sz + N4);
   int* hdr = sid + N4;                        // [0] = axis
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  float* cand_d = reinterpret_cast<float*>(hdr + 4) + (size_t)warp * KNN_BUF;
-  int* cand_i = reinterpret_cast<int*>(reinterpret_cast<float*>(hdr + 4) + (size_t)nwarps * KNN_BUF) + (size_t)warp * KNN_BUF;
+  float* cand_d = reinterpret_cast<float*>(hdr + 8 + KNN_MAX_STRIPS) + (size_t)warp * KNN_BUF;
+  int* cand_i = reinterpret_cast<int*>(reinterpret_cast<float*>(hdr + 8 + KNN_MAX_STRIPS) + (size_t)nwarps * KNN_BUF) + (size_t)warp * KNN_BUF;
   __shared__ __align__(8) uint64_t bar;
 
   const int b = blockIdx.y;
@@ -452,8 +509,9 @@ knn_slab_kernel(const float* __restrict__ ws, const int* __restrict__ qorder, co
   const bool do_warp = warp_qt != nullptr;
   if (do_warp) pose = make_pose(warp_qt + (size_t)b * 7);
   slab_mbar_wait(&bar, 0);
-  const int axis = hdr[0];
-  const float* sa = axis == 0 ? sx : (axis == 1 ? sy : sz);
+  const int axis = hdr[0], axis2 = hdr[1], strips = hdr[2], logL = hdr[3];
+  const float* sa1b = reinterpret_cast<const float*>(hdr + 4);     // strip bounds along a1 [strips + 1]
+  const float* sa = axis2 == 0 ? sx : (axis2 == 1 ? sy : sz);     // in-strip sort axis a2
 
   const int flush_at = min(32, max(2 * K, 8));
   // each warp walks a contiguous run of the (Morton-ordered) query list of this CTA
@@ -481,54 +539,73 @@ knn_slab_kernel(const float* __restrict__ ws, const int* __restrict__ qorder, co
       bound0 = __fmul_ru(__fmul_ru(rr, rr), 1.00002f);
     }
     pqx = qx; pqy = qy; pqz = qz;
-    const float qa = axis == 0 ? qx : (axis == 1 ? qy : qz);
-    // first sorted position with sa[pos] >= qa
-    int lo_b = 0, hi_b = N;
-    while (lo_b < hi_b) {
-      const int mid = (lo_b + hi_b) >> 1;
-      if (sa[mid] < qa) lo_b = mid + 1; else hi_b = mid;
-    }
-    int left = lo_b - 1, right = lo_b;   // nearest unscanned positions on each side
+    const float qa1 = axis == 0 ? qx : (axis == 1 ? qy : qz);
+    const float qa = axis2 == 0 ? qx : (axis2 == 1 ? qy : qz);
+    // squared a1 distance from the query to strip t (0 inside its closed a1 range); monotone in fp32
+    auto strip_d1 = [&](int t) -> float {
+      const float d = fmaxf(fmaxf(__fsub_rn(sa1b[t], qa1), __fsub_rn(qa1, sa1b[t + 1])), 0.f);
+      return __fmul_rn(d, d);
+    };
+    // home strip: the last one whose first point is not beyond the query
+    int t = __popc(__ballot_sync(PWCLO_FULL_MASK, lane >= 1 && lane < strips && sa1b[lane] <= qa1));
+    int tl = t - 1, tr = t + 1;
+    float d1 = strip_d1(t);
     u64 list = KNN_INF_KEY;
     float bound = bound0;
     int cnt = 0;
-    while (left >= 0 || right < N) {
-      float el = CUDART_INF_F, er = CUDART_INF_F;   // squared axis distance of the nearest unscanned point
-      if (left >= 0) { const float d = __fsub_rn(qa, sa[left]); el = __fmul_rn(d, d); }
-      if (right < N) { const float d = __fsub_rn(qa, sa[right]); er = __fmul_rn(d, d); }
-      const bool go_left = el <= er;
-      const float e = go_left ? el : er;
-      if (!(e <= bound)) break;          // both sides exhausted or provably too far (also ends on inf/inf)
-      int pos;
-      if (go_left) { pos = left - lane; left -= 32; }
-      else { pos = right + lane; right += 32; }
-      const bool rv = pos >= 0 && pos < N;
-      const int pc = rv ? pos : 0;
-      const float dx = __fsub_rn(qx, sx[pc]), dy = __fsub_rn(qy, sy[pc]), dz = __fsub_rn(qz, sz[pc]);
-      const float xx = __fmul_rn(dx, dx), yy = __fmul_rn(dy, dy), zz = __fmul_rn(dz, dz);
-      const float d2 = SUM_ORDER == 0 ? __fadd_rn(__fadd_rn(xx, yy), zz) : __fadd_rn(__fadd_rn(xx, zz), yy);
-      const bool pass = rv && d2 <= bound;
-      const unsigned mask = __ballot_sync(PWCLO_FULL_MASK, pass);
-      if (mask) {
-        if (pass) {
-          const int slot = cnt + __popc(mask & ((1u << lane) - 1u));
-          cand_d[slot] = d2;
-          cand_i[slot] = sid[pc];
-        }
-        cnt += __popc(mask);
-        if (cnt >= flush_at) {   // small K: merge early so that the pruning bound tightens early
-          __syncwarp();
-          const u64 ck = lane < cnt ? knn_key(__fsqrt_rn(__fadd_rn(cand_d[lane], 1e-8f)), cand_i[lane]) : KNN_INF_KEY;
-          const int rest = max(cnt - 32, 0);
-          float md = 0.f; int mi = 0;
-          if (lane < rest) { md = cand_d[32 + lane]; mi = cand_i[32 + lane]; }
-          __syncwarp();
-          if (lane < rest) { cand_d[lane] = md; cand_i[lane] = mi; }
-          cnt = rest;
-          list = knn_merge32(list, ck, lane);
-          bound = fminf(bound, knn_bound(__uint_as_float((unsigned)(shfl_u64(list, K - 1) >> 32))));
+    while (true) {
+      const int s_begin = t << logL, s_end = min(N, s_begin + (1 << logL));
+      // first position of the strip with sa[pos] >= qa
+      int lo_b = s_begin, hi_b = s_end;
+      while (lo_b < hi_b) {
+        const int mid = (lo_b + hi_b) >> 1;
+        if (sa[mid] < qa) lo_b = mid + 1; else hi_b = mid;
+      }
+      int left = lo_b - 1, right = lo_b;   // nearest unscanned positions on each side
+      while (left >= s_begin || right < s_end) {
+        float el = CUDART_INF_F, er = CUDART_INF_F;   // squared a2 distance of the nearest unscanned point
+        if (left >= s_begin) { const float d = __fsub_rn(qa, sa[left]); el = __fmul_rn(d, d); }
+        if (right < s_end) { const float d = __fsub_rn(qa, sa[right]); er = __fmul_rn(d, d); }
+        const bool go_left = el <= er;
+        const float e = go_left ? el : er;
+        if (!(__fadd_rd(e, d1) <= bound)) break;          // both sides exhausted or provably too far (also ends on inf)
+        int pos;
+        bool rv;
+        if (go_left) { pos = left - lane; left -= 32; rv = pos >= s_begin; }
+        else { pos = right + lane; right += 32; rv = pos < s_end; }
+        const int pc = rv ? pos : s_begin;
+        const float dx = __fsub_rn(qx, sx[pc]), dy = __fsub_rn(qy, sy[pc]), dz = __fsub_rn(qz, sz[pc]);
+        const float xx = __fmul_rn(dx, dx), yy = __fmul_rn(dy, dy), zz = __fmul_rn(dz, dz);
+        const float d2 = SUM_ORDER == 0 ? __fadd_rn(__fadd_rn(xx, yy), zz) : __fadd_rn(__fadd_rn(xx, zz), yy);
+        const bool pass = rv && d2 <= bound;
+        const unsigned mask = __ballot_sync(PWCLO_FULL_MASK, pass);
+        if (mask) {
+          if (pass) {
+            const int slot = cnt + __popc(mask & ((1u << lane) - 1u));
+            cand_d[slot] = d2;
+            cand_i[slot] = sid[pc];
+          }
+          cnt += __popc(mask);
+          if (cnt >= flush_at) {   // small K: merge early so that the pruning bound tightens early
+            __syncwarp();
+            const u64 ck = lane < cnt ? knn_key(__fsqrt_rn(__fadd_rn(cand_d[lane], 1e-8f)), cand_i[lane]) : KNN_INF_KEY;
+            const int rest = max(cnt - 32, 0);
+            float md = 0.f; int mi = 0;
+            if (lane < rest) { md = cand_d[32 + lane]; mi = cand_i[32 + lane]; }
+            __syncwarp();
+            if (lane < rest) { cand_d[lane] = md; cand_i[lane] = mi; }
+            cnt = rest;
+            list = knn_merge32(list, ck, lane);
+            bound = fminf(bound, knn_bound(__uint_as_float((unsigned)(shfl_u64(list, K - 1) >> 32))));
+          }
         }
       }
+      // next strip: the nearer of the two unvisited neighbours along a1
+      if (tl < 0 && tr >= strips) break;
+      const float dl = tl >= 0 ? strip_d1(tl) : CUDART_INF_F;
+      const float dr = tr < strips ? strip_d1(tr) : CUDART_INF_F;
+      if (tl >= 0 && (dl <= dr || tr >= strips)) { t = tl--; d1 = dl; } else { t = tr++; d1 = dr; }
+      if (!(d1 <= bound)) break;        // every remaining strip is provably too far
     }
     if (cnt > 0) {
       __syncwarp();
@@ -591,8 +668,8 @@ knn_slab_small_kernel(const float* __restrict__ ws, const float* __restrict__ ne
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane / G, gl = lane % G;
   const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (grp * G);
-  float* cand_d = reinterpret_cast<float*>(hdr + 4) + (size_t)warp * KNN_BUF + grp * 2 * G;
-  int* cand_i = reinterpret_cast<int*>(reinterpret_cast<float*>(hdr + 4) + (size_t)SLAB_WARPS * KNN_BUF) + (size_t)warp * KNN_BUF + grp * 2 * G;
+  float* cand_d = reinterpret_cast<float*>(hdr + 8 + KNN_MAX_STRIPS) + (size_t)warp * KNN_BUF + grp * 2 * G;
+  int* cand_i = reinterpret_cast<int*>(reinterpret_cast<float*>(hdr + 8 + KNN_MAX_STRIPS) + (size_t)SLAB_WARPS * KNN_BUF) + (size_t)warp * KNN_BUF + grp * 2 * G;
   __shared__ __align__(8) uint64_t bar;
 
   const int b = blockIdx.y;
@@ -614,10 +691,10 @@ knn_slab_small_kernel(const float* __restrict__ ws, const float* __restrict__ ne
   const bool do_warp = warp_qt != nullptr;
   if (do_warp) pose = make_pose(warp_qt + (size_t)b * 7);
   slab_mbar_wait(&bar, 0);
-  const int axis = hdr[0];
-  const float* sa = axis == 0 ? sx : (axis == 1 ? sy : sz);
-  int nsearch = 1;                       // binary-search steps: enough for N + 1 outcomes
-  while ((1 << nsearch) < N + 1) ++nsearch;
+  const int axis = hdr[0], axis2 = hdr[1], strips = hdr[2], logL = hdr[3];
+  const float* sa1b = reinterpret_cast<const float*>(hdr + 4);     // strip bounds along a1 [strips + 1]
+  const float* sa = axis2 == 0 ? sx : (axis2 == 1 ? sy : sz);     // in-strip sort axis a2
+  const int nsearch = logL + 1;          // binary-search steps inside a strip: enough for 2^logL + 1 outcomes
 
   const int flush_at = min(G, max(2 * K, 8));
   const int c_begin = blockIdx.x * q_per_cta, c_end = min(S, c_begin + q_per_cta);
@@ -633,33 +710,71 @@ knn_slab_small_kernel(const float* __restrict__ ws, const float* __restrict__ ne
         o[0] = qx; o[1] = qy; o[2] = qz;
       }
     }
-    const float qa = axis == 0 ? qx : (axis == 1 ? qy : qz);
-    int lo_b = 0, hi_b = N;              // first sorted position with sa[pos] >= qa (fixed trip count: no divergence)
-    for (int it = 0; it < nsearch; ++it) {
-      const int mid = (lo_b + hi_b) >> 1;
-      const bool go = lo_b < hi_b && sa[min(mid, N - 1)] < qa;
-      const bool stay = lo_b < hi_b && !go;
-      lo_b = go ? mid + 1 : lo_b;
-      hi_b = stay ? mid : hi_b;
+    const float qa1 = axis == 0 ? qx : (axis == 1 ? qy : qz);
+    const float qa = axis2 == 0 ? qx : (axis2 == 1 ? qy : qz);
+    auto strip_d1 = [&](int t) -> float {
+      const float d = fmaxf(fmaxf(__fsub_rn(sa1b[t], qa1), __fsub_rn(qa1, sa1b[t + 1])), 0.f);
+      return __fmul_rn(d, d);
+    };
+    // per-group state (uniform inside a group): current strip t with a1 distance d1, scan cursors, next strips
+    int t = __popc(__ballot_sync(PWCLO_FULL_MASK, gl >= 1 && gl < strips && sa1b[gl] <= qa1) & gmask);   // home strip
+    if (G < KNN_MAX_STRIPS)
+      t += __popc(__ballot_sync(PWCLO_FULL_MASK, gl + G < strips && sa1b[gl + G] <= qa1) & gmask);
+    if (2 * G < KNN_MAX_STRIPS) {
+      t += __popc(__ballot_sync(PWCLO_FULL_MASK, gl + 2 * G < strips && sa1b[gl + 2 * G] <= qa1) & gmask);
+      t += __popc(__ballot_sync(PWCLO_FULL_MASK, gl + 3 * G < strips && sa1b[gl + 3 * G] <= qa1) & gmask);
     }
-    int left = lo_b - 1, right = lo_b;
+    int tl = t - 1, tr = t + 1;
+    float d1 = strip_d1(t);
+    int s_begin, s_end, left, right;
+    bool done = !has_q;
+    // enter strip t: binary search of the query's a2 position (no warp collectives inside: may diverge)
+    auto enter = [&]() {
+      s_begin = t << logL;
+      s_end = min(N, s_begin + (1 << logL));
+      int lo_b = s_begin, hi_b = s_end;
+      while (lo_b < hi_b) {
+        const int mid = (lo_b + hi_b) >> 1;
+        if (sa[mid] < qa) lo_b = mid + 1; else hi_b = mid;
+      }
+      left = lo_b - 1; right = lo_b;
+    };
+    enter();
     u64 list = KNN_INF_KEY;
     float bound = CUDART_INF_F;
     int cnt = 0;
     while (true) {
-      float el = CUDART_INF_F, er = CUDART_INF_F;
-      if (left >= 0) { const float d = __fsub_rn(qa, sa[left]); el = __fmul_rn(d, d); }
-      if (right < N) { const float d = __fsub_rn(qa, sa[right]); er = __fmul_rn(d, d); }
-      const bool go_left = el <= er;
-      const float e = go_left ? el : er;
-      const bool active = has_q && (left >= 0 || right < N) && e <= bound;   // uniform within a group
-      if (!__any_sync(PWCLO_FULL_MASK, active)) break;
-      int pos = 0;
-      if (active) {
-        if (go_left) { pos = left - gl; left -= G; }
-        else { pos = right + gl; right += G; }
+      float e;
+      bool go_left, active;
+      // nearest unscanned point of the current strip and whether it can still matter
+      auto probe = [&]() {
+        float el = CUDART_INF_F, er = CUDART_INF_F;
+        if (left >= s_begin) { const float d = __fsub_rn(qa, sa[left]); el = __fmul_rn(d, d); }
+        if (right < s_end) { const float d = __fsub_rn(qa, sa[right]); er = __fmul_rn(d, d); }
+        go_left = el <= er;
+        e = go_left ? el : er;
+        active = (left >= s_begin || right < s_end) && __fadd_rd(e, d1) <= bound;   // uniform within a group
+      };
+      probe();
+      if (!done && !active) {
+        // strip finished: move to the nearer unvisited neighbour strip along a1, or stop
+        if (tl < 0 && tr >= strips) {
+          done = true;
+        } else {
+          const float dl = tl >= 0 ? strip_d1(tl) : CUDART_INF_F;
+          const float dr = tr < strips ? strip_d1(tr) : CUDART_INF_F;
+          if (tl >= 0 && (dl <= dr || tr >= strips)) { t = tl--; d1 = dl; } else { t = tr++; d1 = dr; }
+          if (d1 <= bound) { enter(); probe(); } else done = true;
+        }
       }
-      const bool rv = active && pos >= 0 && pos < N;
+      active = active && !done;
+      if (!__any_sync(PWCLO_FULL_MASK, !done)) break;
+      int pos = 0;
+      bool rv = false;
+      if (active) {
+        if (go_left) { pos = left - gl; left -= G; rv = pos >= s_begin; }
+        else { pos = right + gl; right += G; rv = pos < s_end; }
+      }
       const int pc = rv ? pos : 0;
       const float dx = __fsub_rn(qx, sx[pc]), dy = __fsub_rn(qy, sy[pc]), dz = __fsub_rn(qz, sz[pc]);
       const float xx = __fmul_rn(dx, dx), yy = __fmul_rn(dy, dy), zz = __fmul_rn(dz, dz);
@@ -736,7 +851,9 @@ PWCLO_API int pwclo_knn_sorted(const float* xyz, const float* new_xyz, int B, in
       cudaError_t e = cudaFuncSetAttribute(knn_presort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
-    knn_presort_kernel<<<B, SORT_THREADS, smem, st>>>(xyz, N, NP, (float*)workspace, new_xyz, S, SP, qorder);
+    const char* se = getenv("PWCLO_KNN_STRIPS");
+    knn_presort_kernel<<<B, SORT_THREADS, smem, st>>>(xyz, N, NP, knn_log_strip(NP, K, se ? atoi(se) : 0), (float*)workspace,
+                                                      new_xyz, S, SP, qorder);
     qorder_used = qorder;
     int rc = launch_status();
     if (rc) return rc;

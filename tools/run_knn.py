@@ -18,6 +18,13 @@ i2 = _ext.furthest_point_sampling(x2, max(S, N)).long()
 g = lambda x, i, n: torch.gather(x, 1, i[:, :n, None].expand(-1, -1, 3)).contiguous()
 q = g(x1, i1, S)
 r = q if "self" in sys.argv else g(x2, i2, N)
+if "rot" in sys.argv:      # a garbage pose estimate: the query cloud is rotated away from the reference cloud
+    ang = 1.0
+    R = torch.tensor([[1, 0, 0], [0, float(torch.cos(torch.tensor(ang))), -float(torch.sin(torch.tensor(ang)))],
+                      [0, float(torch.sin(torch.tensor(ang))), float(torch.cos(torch.tensor(ang)))]], device=dev)
+    q = (q @ R.T).contiguous() + torch.tensor([3.0, -2.0, 5.0], device=dev)
+if "brute" in sys.argv:
+    _ext.KNN_SORTED = False
 for _ in range(3):
     _ext.knn(r, q, K)
 torch.cuda.synchronize()
