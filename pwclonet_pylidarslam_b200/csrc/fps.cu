@@ -388,12 +388,14 @@ PWCLO_API int pwclo_furthest_point_sampling(const float* xyz, int B, int N, int 
   const int skip = (flags & PWCLO_FPS_ORIGIN_SKIP) ? 1 : 0;
   // THREADS must be a multiple of T so that a thread's points share (k mod T): 512 or 1024 (cap 1024)
   // slab-skipping kernel: worth its two in-kernel sorts once there are enough rounds and points
-  if (m >= 256 && N > 2048 && !getenv("PWCLO_FPS_NO_SLAB")) {
+  const char* slab_min = getenv("PWCLO_FPS_SLAB_MIN_N");
+  if (m >= 256 && N >= (slab_min ? atoi(slab_min) : 2049) && !getenv("PWCLO_FPS_NO_SLAB")) {
     const bool wide = getenv("PWCLO_FPS_SLAB8") == nullptr;     // 512 threads x 16 points: fewer warps per barrier (7 % faster)
     if (cap == 1024) {
       if (N <= 4096) return launch_fps_slab<4, 1024>(xyz, B, N, m, logT, skip, idx, st);
       if (N <= 8192) return launch_fps_slab<8, 1024>(xyz, B, N, m, logT, skip, idx, st);
     } else {
+      if (N <= 2048) return launch_fps_slab<4, 512>(xyz, B, N, m, logT, skip, idx, st);
       if (N <= 4096) return launch_fps_slab<8, 512>(xyz, B, N, m, logT, skip, idx, st);
       if (N <= 8192) return wide ? launch_fps_slab<16, 512>(xyz, B, N, m, logT, skip, idx, st)
                                  : launch_fps_slab<8, 1024>(xyz, B, N, m, logT, skip, idx, st);

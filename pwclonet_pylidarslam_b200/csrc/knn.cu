@@ -289,6 +289,29 @@ __host__ __device__ inline int knn_log_strip(int NP, int K, int strips_req) {
   return logL;
 }
 
+// In-place bitonic sort network on shared-memory keys, stages k = 2 .. kmax (kmax < NP sorts every aligned
+// kmax-block on its own, all ascending).  Every warp owns a contiguous run of compare-exchange pairs,
+// so the sub-steps whose partner distance stays inside a warp's run need __syncwarp only.
+__device__ __forceinline__ void knn_bitonic(u64* keys, int NP, int kmax, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const int ppw = max(NP / 2 / (SORT_THREADS / 32), 32);      // pairs per warp
+  const int t_begin = warp * ppw, t_end = min(NP / 2, t_begin + ppw);
+  for (int k = 2; k <= kmax; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = t_begin + lane; t < t_end; t += 32) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j cleared
+        const int hi = lo | j;
+        const u64 a = keys[lo], c = keys[hi];
+        const bool up = k == kmax || (lo & k) == 0;             // last stage: every block ascending
+        if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
+      }
+      const int jn = j > 1 ? (j >> 1) : k;                      // partner distance of the next sub-step
+      if (j <= ppw && jn <= ppw) __syncwarp(); else __syncthreads();
+    }
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(SORT_THREADS)
 knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, int logL, float* __restrict__ ws,
                    const float* __restrict__ queries, int S, int SP, int* __restrict__ qorder) {
@@ -335,18 +358,7 @@ knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, int logL, float
   for (int i = tid; i < NP; i += SORT_THREADS)
     keys[i] = i < N ? (((u64)ordered_bits(xyz[i * 3 + axis]) << 32) | (unsigned)i) : ~0ull;
   __syncthreads();
-  for (int k = 2; k <= NP; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < NP / 2; t += SORT_THREADS) {
-        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j cleared
-        const int hi = lo | j;
-        const u64 a = keys[lo], c = keys[hi];
-        const bool up = (lo & k) == 0;
-        if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
-      }
-      __syncthreads();
-    }
-  }
+  knn_bitonic(keys, NP, NP, tid);
   const int N4 = (N + 3) & ~3;
   float* w = ws + (size_t)b * knn_ws_stride(N);
   // ---- strips: equal-count cuts of the a1 order; bounds[t] = a1 of the first point of strip t,
@@ -372,18 +384,7 @@ knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, int logL, float
     keys[i] = k2;
   }
   __syncthreads();
-  for (int k = 2; k <= L; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < NP / 2; t += SORT_THREADS) {
-        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int hi = lo | j;
-        const u64 a = keys[lo], c = keys[hi];
-        const bool up = k == L || (lo & k) == 0;      // last stage: every strip ascending
-        if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
-      }
-      __syncthreads();
-    }
-  }
+  knn_bitonic(keys, NP, L, tid);
   for (int i = tid; i < N4; i += SORT_THREADS) {
     float x = CUDART_INF_F, y = CUDART_INF_F, z = CUDART_INF_F;
     int id = 0;
