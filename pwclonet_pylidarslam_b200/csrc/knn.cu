@@ -74,6 +74,10 @@ __device__ __noinline__ u64 knn_merge32(u64 list, u64 cand, int lane) {
   return c;
 }
 
+// rd(rd(e1 + e3) + e2) * KNN_LB_SLACK > bound  =>  d2 = rn(rn(A + B) + C) > bound for any association of the
+// three squared components with e_i <= its component: the exact sum T >= the rounded-down sum, d2 >= T (1 - 2^-23)
+constexpr float KNN_LB_SLACK = 0.99999976f;   // 1 - 2^-22
+
 // Conservative squared-distance bound: d2 > bound  =>  sqrt_rn(d2 + 1e-8f) >= kth  
 __device__ __forceinline__ float knn_bound(float kth) { return __fmul_ru(__fmul_ru(kth, kth), 1.0000005f); }
 
@@ -276,8 +280,10 @@ __device__ __forceinline__ unsigned ordered_bits(float f) {
 }
 
 constexpr int KNN_MAX_STRIPS = 32;
-// floats per cloud: x | y | z | id (N4 each) | hdr (axis1, axis2, strips, log2 strip length) | strip bounds (KNN_MAX_STRIPS + 4)
-__host__ __device__ inline size_t knn_ws_stride(int N) { return (size_t)4 * ((N + 3) & ~3) + 4 + KNN_MAX_STRIPS + 4; }
+// floats per cloud: x | y | z | id (N4 each) | hdr (axis1, axis2, strips, log2 strip length) | a1 bounds of the strips
+// (KNN_MAX_STRIPS + 4) | per-strip min / max of the third axis a3 (KNN_MAX_STRIPS each)
+constexpr int KNN_HDR = 4 + (KNN_MAX_STRIPS + 4) + 2 * KNN_MAX_STRIPS;
+__host__ __device__ inline size_t knn_ws_stride(int N) { return (size_t)4 * ((N + 3) & ~3) + KNN_HDR; }
 // strips for a cloud padded to NP (power of two) points
 __host__ __device__ inline int knn_log_strip(int NP, int K, int strips_req) {
   // measured on B200 (tools/run_knn.py): 16 strips for the big clouds, 8 when 32 neighbours are wanted from 2048 points
@@ -395,6 +401,23 @@ knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, int logL, float
     w[i] = x; w[N4 + i] = y; w[2 * N4 + i] = z;
     reinterpret_cast<int*>(w)[3 * N4 + i] = id;
   }
+  // ---- range of the third axis inside every strip (one warp per strip): a 3-D lower bound for the search
+  if (warp < strips) {
+    const int axis3 = 3 - axis - axis2;
+    float lo3 = CUDART_INF_F, hi3 = -CUDART_INF_F;
+    for (int i = (warp << logL) + lane; i < min(N, (warp + 1) << logL); i += 32) {
+      const float v = xyz[(int)((unsigned)keys[i] & 0x1fffu) * 3 + axis3];
+      lo3 = fminf(lo3, v); hi3 = fmaxf(hi3, v);
+    }
+    for (int off = 16; off; off >>= 1) {
+      lo3 = fminf(lo3, __shfl_xor_sync(PWCLO_FULL_MASK, lo3, off));
+      hi3 = fmaxf(hi3, __shfl_xor_sync(PWCLO_FULL_MASK, hi3, off));
+    }
+    if (lane == 0) {
+      w[4 * N4 + 4 + KNN_MAX_STRIPS + 4 + warp] = lo3;
+      w[4 * N4 + 4 + 2 * KNN_MAX_STRIPS + 4 + warp] = hi3;
+    }
+  }
 
   // ---- query visiting order: Morton order (6 bits per axis) of the queries of this cloud, so that the
   // queries a warp processes back to back are neighbours in space (their K-th distance + their mutual
@@ -487,8 +510,8 @@ knn_slab_kernel(const float* __restrict__ ws, const int* __restrict__ qorder, co
   int* sid = reinterpret_cast<int*>(sz + N4);
   int* hdr = sid + N4;                        // [0] = axis
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  float* cand_d = reinterpret_cast<float*>(hdr + 8 + KNN_MAX_STRIPS) + (size_t)warp * KNN_BUF;
-  int* cand_i = reinterpret_cast<int*>(reinterpret_cast<float*>(hdr + 8 + KNN_MAX_STRIPS) + (size_t)nwarps * KNN_BUF) + (size_t)warp * KNN_BUF;
+  float* cand_d = reinterpret_cast<float*>(hdr + KNN_HDR) + (size_t)warp * KNN_BUF;
+  int* cand_i = reinterpret_cast<int*>(reinterpret_cast<float*>(hdr + KNN_HDR) + (size_t)nwarps * KNN_BUF) + (size_t)warp * KNN_BUF;
   __shared__ __align__(8) uint64_t bar;
 
   const int b = blockIdx.y;
@@ -512,6 +535,9 @@ knn_slab_kernel(const float* __restrict__ ws, const int* __restrict__ qorder, co
   slab_mbar_wait(&bar, 0);
   const int axis = hdr[0], axis2 = hdr[1], strips = hdr[2], logL = hdr[3];
   const float* sa1b = reinterpret_cast<const float*>(hdr + 4);     // strip bounds along a1 [strips + 1]
+  const float* sa3lo = sa1b + KNN_MAX_STRIPS + 4;                   // per-strip range of the third axis
+  const float* sa3hi = sa3lo + KNN_MAX_STRIPS;
+  const int axis3 = 3 - axis - axis2;
   const float* sa = axis2 == 0 ? sx : (axis2 == 1 ? sy : sz);     // in-strip sort axis a2
 
   const int flush_at = min(32, max(2 * K, 8));
@@ -542,19 +568,28 @@ knn_slab_kernel(const float* __restrict__ ws, const int* __restrict__ qorder, co
     pqx = qx; pqy = qy; pqz = qz;
     const float qa1 = axis == 0 ? qx : (axis == 1 ? qy : qz);
     const float qa = axis2 == 0 ? qx : (axis2 == 1 ? qy : qz);
+    const float qa3 = axis3 == 0 ? qx : (axis3 == 1 ? qy : qz);
     // squared a1 distance from the query to strip t (0 inside its closed a1 range); monotone in fp32
     auto strip_d1 = [&](int t) -> float {
       const float d = fmaxf(fmaxf(__fsub_rn(sa1b[t], qa1), __fsub_rn(qa1, sa1b[t + 1])), 0.f);
       return __fmul_rn(d, d);
     };
+    // ... plus the squared a3 distance to the strip's a3 range, summed downwards: a lower bound (up to the
+    // association order of the three terms, covered by KNN_LB_SLACK) of d2 for every point of strip t
+    auto strip_d13 = [&](int t, float e1) -> float {
+      const float d = fmaxf(fmaxf(__fsub_rn(sa3lo[t], qa3), __fsub_rn(qa3, sa3hi[t])), 0.f);
+      return __fadd_rd(e1, __fmul_rn(d, d));
+    };
     // home strip: the last one whose first point is not beyond the query
     int t = __popc(__ballot_sync(PWCLO_FULL_MASK, lane >= 1 && lane < strips && sa1b[lane] <= qa1));
     int tl = t - 1, tr = t + 1;
     float d1 = strip_d1(t);
+    float d13 = strip_d13(t, d1);
     u64 list = KNN_INF_KEY;
     float bound = bound0;
     int cnt = 0;
     while (true) {
+     if (__fmul_rd(d13, KNN_LB_SLACK) <= bound) {      // otherwise the whole strip is provably too far (a3 range)
       const int s_begin = t << logL, s_end = min(N, s_begin + (1 << logL));
       // first position of the strip with sa[pos] >= qa
       int lo_b = s_begin, hi_b = s_end;
@@ -569,7 +604,7 @@ knn_slab_kernel(const float* __restrict__ ws, const int* __restrict__ qorder, co
         if (right < s_end) { const float d = __fsub_rn(qa, sa[right]); er = __fmul_rn(d, d); }
         const bool go_left = el <= er;
         const float e = go_left ? el : er;
-        if (!(__fadd_rd(e, d1) <= bound)) break;          // both sides exhausted or provably too far (also ends on inf)
+        if (!(__fmul_rd(__fadd_rd(e, d13), KNN_LB_SLACK) <= bound)) break;   // provably too far (also ends on inf)
         int pos;
         bool rv;
         if (go_left) { pos = left - lane; left -= 32; rv = pos >= s_begin; }
@@ -601,12 +636,14 @@ knn_slab_kernel(const float* __restrict__ ws, const int* __restrict__ qorder, co
           }
         }
       }
+     }
       // next strip: the nearer of the two unvisited neighbours along a1
       if (tl < 0 && tr >= strips) break;
       const float dl = tl >= 0 ? strip_d1(tl) : CUDART_INF_F;
       const float dr = tr < strips ? strip_d1(tr) : CUDART_INF_F;
       if (tl >= 0 && (dl <= dr || tr >= strips)) { t = tl--; d1 = dl; } else { t = tr++; d1 = dr; }
-      if (!(d1 <= bound)) break;        // every remaining strip is provably too far
+      if (!(d1 <= bound)) break;        // every remaining strip is provably too far along a1 alone
+      d13 = strip_d13(t, d1);
     }
     if (cnt > 0) {
       __syncwarp();
@@ -669,8 +706,8 @@ knn_slab_small_kernel(const float* __restrict__ ws, const float* __restrict__ ne
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane / G, gl = lane % G;
   const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (grp * G);
-  float* cand_d = reinterpret_cast<float*>(hdr + 8 + KNN_MAX_STRIPS) + (size_t)warp * KNN_BUF + grp * 2 * G;
-  int* cand_i = reinterpret_cast<int*>(reinterpret_cast<float*>(hdr + 8 + KNN_MAX_STRIPS) + (size_t)SLAB_WARPS * KNN_BUF) + (size_t)warp * KNN_BUF + grp * 2 * G;
+  float* cand_d = reinterpret_cast<float*>(hdr + KNN_HDR) + (size_t)warp * KNN_BUF + grp * 2 * G;
+  int* cand_i = reinterpret_cast<int*>(reinterpret_cast<float*>(hdr + KNN_HDR) + (size_t)SLAB_WARPS * KNN_BUF) + (size_t)warp * KNN_BUF + grp * 2 * G;
   __shared__ __align__(8) uint64_t bar;
 
   const int b = blockIdx.y;
@@ -694,6 +731,9 @@ knn_slab_small_kernel(const float* __restrict__ ws, const float* __restrict__ ne
   slab_mbar_wait(&bar, 0);
   const int axis = hdr[0], axis2 = hdr[1], strips = hdr[2], logL = hdr[3];
   const float* sa1b = reinterpret_cast<const float*>(hdr + 4);     // strip bounds along a1 [strips + 1]
+  const float* sa3lo = sa1b + KNN_MAX_STRIPS + 4;                   // per-strip range of the third axis
+  const float* sa3hi = sa3lo + KNN_MAX_STRIPS;
+  const int axis3 = 3 - axis - axis2;
   const float* sa = axis2 == 0 ? sx : (axis2 == 1 ? sy : sz);     // in-strip sort axis a2
   const int nsearch = logL + 1;          // binary-search steps inside a strip: enough for 2^logL + 1 outcomes
 
@@ -713,9 +753,16 @@ knn_slab_small_kernel(const float* __restrict__ ws, const float* __restrict__ ne
     }
     const float qa1 = axis == 0 ? qx : (axis == 1 ? qy : qz);
     const float qa = axis2 == 0 ? qx : (axis2 == 1 ? qy : qz);
+    const float qa3 = axis3 == 0 ? qx : (axis3 == 1 ? qy : qz);
     auto strip_d1 = [&](int t) -> float {
       const float d = fmaxf(fmaxf(__fsub_rn(sa1b[t], qa1), __fsub_rn(qa1, sa1b[t + 1])), 0.f);
       return __fmul_rn(d, d);
+    };
+    // ... plus the squared a3 distance to the strip's a3 range, summed downwards: a lower bound (up to the
+    // association order of the three terms, covered by KNN_LB_SLACK) of d2 for every point of strip t
+    auto strip_d13 = [&](int t, float e1) -> float {
+      const float d = fmaxf(fmaxf(__fsub_rn(sa3lo[t], qa3), __fsub_rn(qa3, sa3hi[t])), 0.f);
+      return __fadd_rd(e1, __fmul_rn(d, d));
     };
     // per-group state (uniform inside a group): current strip t with a1 distance d1, scan cursors, next strips
     int t = __popc(__ballot_sync(PWCLO_FULL_MASK, gl >= 1 && gl < strips && sa1b[gl] <= qa1) & gmask);   // home strip
@@ -727,6 +774,7 @@ knn_slab_small_kernel(const float* __restrict__ ws, const float* __restrict__ ne
     }
     int tl = t - 1, tr = t + 1;
     float d1 = strip_d1(t);
+    float d13 = strip_d13(t, d1);
     int s_begin, s_end, left, right;
     bool done = !has_q;
     // enter strip t: binary search of the query's a2 position (no warp collectives inside: may diverge)
@@ -754,7 +802,7 @@ knn_slab_small_kernel(const float* __restrict__ ws, const float* __restrict__ ne
         if (right < s_end) { const float d = __fsub_rn(qa, sa[right]); er = __fmul_rn(d, d); }
         go_left = el <= er;
         e = go_left ? el : er;
-        active = (left >= s_begin || right < s_end) && __fadd_rd(e, d1) <= bound;   // uniform within a group
+        active = (left >= s_begin || right < s_end) && __fmul_rd(__fadd_rd(e, d13), KNN_LB_SLACK) <= bound;   // uniform within a group
       };
       probe();
       if (!done && !active) {
@@ -765,7 +813,13 @@ knn_slab_small_kernel(const float* __restrict__ ws, const float* __restrict__ ne
           const float dl = tl >= 0 ? strip_d1(tl) : CUDART_INF_F;
           const float dr = tr < strips ? strip_d1(tr) : CUDART_INF_F;
           if (tl >= 0 && (dl <= dr || tr >= strips)) { t = tl--; d1 = dl; } else { t = tr++; d1 = dr; }
-          if (d1 <= bound) { enter(); probe(); } else done = true;
+          if (d1 <= bound) {
+            d13 = strip_d13(t, d1);
+            // a strip that is too far by its a3 range alone is left at once: empty cursors, next round advances
+            if (__fmul_rd(d13, KNN_LB_SLACK) <= bound) { enter(); probe(); } else { left = -1; right = 0; s_begin = 0; s_end = 0; active = false; }
+          } else {
+            done = true;
+          }
         }
       }
       active = active && !done;
