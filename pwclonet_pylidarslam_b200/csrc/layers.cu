@@ -126,33 +126,41 @@ __global__ void __launch_bounds__(LT) set_conv_kernel(const SAArgs a) {
 // memory, and the max over the K neighbours is a log-step shuffle transpose-reduce.  No activation
 // ever touches shared memory; the GEMM-tile kernel above wastes most of its tile on these widths.
 // ------------------------------------------------------------------------------------------------
-template <int CIN4, int COUT>
-__device__ __forceinline__ void small_layer(const float (&x)[CIN4], float (&y)[COUT], const float* __restrict__ w,
+template <int R, int CIN4, int COUT>
+__device__ __forceinline__ void small_layer(const float (&x)[R][CIN4], float (&y)[R][COUT], const float* __restrict__ w,
                                             const float* __restrict__ b) {
 #pragma unroll
   for (int n = 0; n < COUT; n += 4) {
     const float4 bv = *reinterpret_cast<const float4*>(b + n);
-    y[n] = bv.x; y[n + 1] = bv.y; y[n + 2] = bv.z; y[n + 3] = bv.w;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { y[r][n] = bv.x; y[r][n + 1] = bv.y; y[r][n + 2] = bv.z; y[r][n + 3] = bv.w; }
   }
 #pragma unroll
   for (int k = 0; k < CIN4; ++k) {
 #pragma unroll
     for (int n = 0; n < COUT; n += 4) {
-      const float4 wv = *reinterpret_cast<const float4*>(w + k * COUT + n);
-      y[n] = fmaf(x[k], wv.x, y[n]);
-      y[n + 1] = fmaf(x[k], wv.y, y[n + 1]);
-      y[n + 2] = fmaf(x[k], wv.z, y[n + 2]);
-      y[n + 3] = fmaf(x[k], wv.w, y[n + 3]);
+      const float4 wv = *reinterpret_cast<const float4*>(w + k * COUT + n);   // one broadcast LDS.128 feeds 4 R FFMAs
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        y[r][n] = fmaf(x[r][k], wv.x, y[r][n]);
+        y[r][n + 1] = fmaf(x[r][k], wv.y, y[r][n + 1]);
+        y[r][n + 2] = fmaf(x[r][k], wv.z, y[r][n + 2]);
+        y[r][n + 3] = fmaf(x[r][k], wv.w, y[r][n + 3]);
+      }
     }
   }
 #pragma unroll
-  for (int n = 0; n < COUT; ++n) y[n] = fmaxf(y[n], 0.f);
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int n = 0; n < COUT; ++n) y[r][n] = fmaxf(y[r][n], 0.f);
 }
 
-template <int K, int C, int C1, int C2, int C3>
+// R rows per lane (the same neighbour slot of R different points): each weight read is shared by R rows,
+// which halves the shared-memory traffic that bounds the one-row version at ~1/3 of the FFMA peak.
+template <int K, int C, int C1, int C2, int C3, int R>
 __global__ void __launch_bounds__(256) set_conv_small_kernel(const SAArgs a, int total_points) {
   constexpr int CIN4 = (C + 3 + 3) & ~3;
-  constexpr int PPW = 32 / K;              // points per warp
+  constexpr int PPW = 32 / K;              // points per warp and row slot
   __shared__ __align__(16) float w1[CIN4 * C1], w2[C1 * C2], w3[C2 * C3], b1[C1], b2[C2], b3[C3];
   for (int i = threadIdx.x; i < CIN4 * C1; i += 256) w1[i] = a.l[0].w[i];
   for (int i = threadIdx.x; i < C1 * C2; i += 256) w2[i] = a.l[1].w[i];
@@ -166,32 +174,37 @@ __global__ void __launch_bounds__(256) set_conv_small_kernel(const SAArgs a, int
   const int warp_global = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * 8;
 #pragma unroll 1
-  for (int g0 = warp_global * PPW; g0 < total_points; g0 += nwarps * PPW) {
+  for (int g0 = warp_global * PPW * R; g0 < total_points; g0 += nwarps * PPW * R) {
     asm volatile("" ::: "memory");                    // keep the (loop-invariant) weights in shared memory, not registers
-    const int g = min(g0 + sub, total_points - 1);    // (cloud, point) flattened
-    const int b = g / a.S;
-    const int n = a.idx[(size_t)g * K + k];
-    const float* q = a.xyz + ((size_t)b * a.N + n) * 3;
-    const float* ctr = a.new_xyz + (size_t)g * 3;
-    float x[CIN4];
-    const float qx = q[0], qy = q[1], qz = q[2];
-    if (a.feats == nullptr) {
-      x[0] = qx; x[1] = qy; x[2] = qz;
-    } else {
-      const float4* f = reinterpret_cast<const float4*>(a.feats + ((size_t)b * a.N + n) * C);
+    float x[R][CIN4];
+    int gr[R];
 #pragma unroll
-      for (int c = 0; c < C / 4; ++c) {
-        const float4 v = __ldg(f + c);
-        x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+    for (int r = 0; r < R; ++r) {
+      const int g = min(g0 + r * PPW + sub, total_points - 1);    // (cloud, point) flattened
+      gr[r] = g;
+      const int b = g / a.S;
+      const int n = a.idx[(size_t)g * K + k];
+      const float* q = a.xyz + ((size_t)b * a.N + n) * 3;
+      const float* ctr = a.new_xyz + (size_t)g * 3;
+      const float qx = q[0], qy = q[1], qz = q[2];
+      if (a.feats == nullptr) {
+        x[r][0] = qx; x[r][1] = qy; x[r][2] = qz;
+      } else {
+        const float4* f = reinterpret_cast<const float4*>(a.feats + ((size_t)b * a.N + n) * C);
+#pragma unroll
+        for (int c = 0; c < C / 4; ++c) {
+          const float4 v = __ldg(f + c);
+          x[r][4 * c] = v.x; x[r][4 * c + 1] = v.y; x[r][4 * c + 2] = v.z; x[r][4 * c + 3] = v.w;
+        }
       }
-    }
-    x[C] = __fsub_rn(qx, ctr[0]); x[C + 1] = __fsub_rn(qy, ctr[1]); x[C + 2] = __fsub_rn(qz, ctr[2]);
+      x[r][C] = __fsub_rn(qx, ctr[0]); x[r][C + 1] = __fsub_rn(qy, ctr[1]); x[r][C + 2] = __fsub_rn(qz, ctr[2]);
 #pragma unroll
-    for (int c = C + 3; c < CIN4; ++c) x[c] = 0.f;
-    float h1[C1], h2[C2], v[C3];
-    small_layer<CIN4, C1>(x, h1, w1, b1);
-    small_layer<C1, C2>(h1, h2, w2, b2);
-    small_layer<C2, C3>(h2, v, w3, b3);
+      for (int c = C + 3; c < CIN4; ++c) x[r][c] = 0.f;
+    }
+    float h1[R][C1], h2[R][C2], v[R][C3];
+    small_layer<R, CIN4, C1>(x, h1, w1, b1);
+    small_layer<R, C1, C2>(h1, h2, w2, b2);
+    small_layer<R, C2, C3>(h2, v, w3, b3);
     // max over the K lanes of a point: transpose-reduce, every step halves the live values per lane
     int nlive = C3, chan = 0;
 #pragma unroll
@@ -200,30 +213,36 @@ __global__ void __launch_bounds__(256) set_conv_small_kernel(const SAArgs a, int
       if (nlive > 1) {
         const int half = nlive / 2;
 #pragma unroll
-        for (int i = 0; i < C3 / 2; ++i) {
-          if (i < half) {
-            const float send = upper ? v[i] : v[i + half];
-            const float keep = upper ? v[i + half] : v[i];
-            v[i] = fmaxf(keep, __shfl_xor_sync(PWCLO_FULL_MASK, send, off));
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int i = 0; i < C3 / 2; ++i) {
+            if (i < half) {
+              const float send = upper ? v[r][i] : v[r][i + half];
+              const float keep = upper ? v[r][i + half] : v[r][i];
+              v[r][i] = fmaxf(keep, __shfl_xor_sync(PWCLO_FULL_MASK, send, off));
+            }
           }
-        }
         chan += upper ? half : 0;
         nlive = half;
       } else {
-        v[0] = fmaxf(v[0], __shfl_xor_sync(PWCLO_FULL_MASK, v[0], off));
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r][0] = fmaxf(v[r][0], __shfl_xor_sync(PWCLO_FULL_MASK, v[r][0], off));
       }
     }
-    // lane now holds `nlive` consecutive channels starting at chan*? (see below)
-    if (g0 + sub < total_points) {
-      float* o = a.out + (size_t)g * C3;
-      if (nlive == 1) {
-        // when K >= C3 several lanes hold the same channel: let the lowest one write
-        const int dup = K / C3 > 1 ? K / C3 : 1;        // lanes per channel
-        if ((k % dup) == 0 || C3 >= K) o[chan] = v[0];
-      } else {
+    // lane now holds `nlive` consecutive channels starting at `chan`
 #pragma unroll
-        for (int i = 0; i < C3; ++i)
-          if (i < nlive) o[chan + i] = v[i];
+    for (int r = 0; r < R; ++r) {
+      if (g0 + r * PPW + sub < total_points) {
+        float* o = a.out + (size_t)gr[r] * C3;
+        if (nlive == 1) {
+          // when K >= C3 several lanes hold the same channel: let the lowest one write
+          const int dup = K / C3 > 1 ? K / C3 : 1;        // lanes per channel
+          if ((k % dup) == 0 || C3 >= K) o[chan] = v[r][0];
+        } else {
+#pragma unroll
+          for (int i = 0; i < C3; ++i)
+            if (i < nlive) o[chan + i] = v[r][i];
+        }
       }
     }
   }
@@ -626,16 +645,21 @@ PWCLO_API int pwclo_set_conv(const float* xyz, const float* feats, const float* 
   if (nlayers == 3 && !getenv("PWCLO_NO_SMALL_SA")) {   // register-resident kernel for the narrow pyramid levels
     const int c1 = a.l[0].cout, c2 = a.l[1].cout, c3 = a.l[2].cout;
     const int total = B * S;
-#define SMALL_CASE(KK, CC, A1, A2, A3)                                                                   \
+#define SMALL_CASE(KK, CC, A1, A2, A3, RR)                                                               \
   if (K == KK && C == CC && c1 == A1 && c2 == A2 && c3 == A3) {                                          \
-    const int ppw = 32 / KK;                                                                             \
+    const int ppw = 32 / KK * RR;                                                                        \
     const int blocks = min(ceil_div(total, 8 * ppw), kNumSM * 8);                                        \
-    set_conv_small_kernel<KK, CC, A1, A2, A3><<<blocks, 256, 0, st>>>(a, total);                         \
+    set_conv_small_kernel<KK, CC, A1, A2, A3, RR><<<blocks, 256, 0, st>>>(a, total);                     \
     return launch_status();                                                                              \
   }
-    SMALL_CASE(32, 3, 8, 8, 16)
-    SMALL_CASE(32, 16, 16, 16, 32)
-    SMALL_CASE(16, 32, 32, 32, 64)
+    const bool one_row = getenv("PWCLO_SA_ONE_ROW") != nullptr;
+    if (!one_row) {
+      SMALL_CASE(32, 3, 8, 8, 16, 2)
+      SMALL_CASE(32, 16, 16, 16, 32, 2)
+    }
+    SMALL_CASE(32, 3, 8, 8, 16, 1)
+    SMALL_CASE(32, 16, 16, 16, 32, 1)
+    SMALL_CASE(16, 32, 32, 32, 64, 1)
 #undef SMALL_CASE
   }
   if (narrow || (smem_for(128) <= 100 * 1024 && K <= 128)) {
