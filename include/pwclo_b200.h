@@ -90,16 +90,26 @@ int pwclo_three_interpolate_grad(const float *grad_out, const int32_t *idx, cons
 int pwclo_knn(const float *xyz, const float *new_xyz, int B, int N, int S, int K, int sum_order,
               const float *warp_qt, float *warped_out, int32_t *idx, float *dist, void *stream);
 
-/* Same contract and bit-identical result as pwclo_knn, but exact search with sorted-slab pruning:
- * the reference points of every cloud are first sorted along their widest axis into `workspace`
- * (pwclo_knn_workspace_bytes(B,N,S) bytes, 16-byte aligned, caller-owned scratch) and the queries into
- * Morton order; each query then scans outwards from its own position only as far as its current K-th
- * distance (initially bounded through the previous, spatially adjacent query) allows.  Falls back to
- * the brute-force kernel when N > 8192 or the workspace is missing / too small. */
+/* Same contract and bit-identical result as pwclo_knn, but exact search with spatial pruning: the
+ * reference points of every cloud are first sorted into `workspace` (pwclo_knn_workspace_bytes(B,N,S)
+ * bytes, 16-byte aligned, caller-owned scratch) -- along their widest axis into equal-count strips,
+ * every strip along the second-widest axis, plus the strips' ranges along the third -- and each query
+ * then visits strips / scans outwards from its own position only as far as its current K-th distance
+ * allows.  Falls back to the brute-force kernel when N > 8192 or the workspace is missing / too small.
+ * The workspace is [B] records of pwclo_knn_workspace_bytes(1,N,0) bytes, so the record range of a
+ * sub-batch can be passed on its own.
+ * pwclo_knn_presort + pwclo_knn_search split the two phases so that several searches against the same
+ * reference clouds (PW/pose_warp_refinement.py:101-148 searches xyz2 of a level twice, xyz1 once more)
+ * share one sort; K of the presort only tunes the strip count. */
 size_t pwclo_knn_workspace_bytes(int B, int N, int S);
 int pwclo_knn_sorted(const float *xyz, const float *new_xyz, int B, int N, int S, int K,
                      int sum_order, const float *warp_qt, float *warped_out, int32_t *idx,
                      float *dist, void *workspace, size_t workspace_bytes, void *stream);
+int pwclo_knn_presort(const float *xyz, int B, int N, int K, void *workspace,
+                      size_t workspace_bytes, void *stream);
+int pwclo_knn_search(const void *workspace, const float *new_xyz, int B, int N, int S, int K,
+                     int sum_order, const float *warp_qt, float *warped_out, int32_t *idx,
+                     float *dist, void *stream);
 
 /* ---- B2: fused inference layers (BatchNorm folded by the host side) ------------------------------
  * Feature tensors are POINT-MAJOR [B,N,C] fp32 (the reference keeps [B,C,N]; pwclo_transpose

@@ -33,6 +33,8 @@ SIGNATURES = {
     "pwclo_three_interpolate_grad": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "pwclo_knn": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pwclo_knn_sorted": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp],
+    "pwclo_knn_presort": [_vp, _i, _i, _i, _vp, ctypes.c_size_t, _vp],
+    "pwclo_knn_search": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pwclo_set_conv": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _LP, _i, _vp, _vp],
     "pwclo_pointwise_mlp": [ctypes.POINTER(_vp), ctypes.POINTER(_i), _i, _i, _LP, _i, _vp, _vp],
     "pwclo_cost_volume_1": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _LP, _LP, _LP, _vp, _vp],

@@ -882,37 +882,25 @@ PWCLO_API size_t pwclo_knn_workspace_bytes(int B, int N, int S) {
   return (size_t)B * knn_ws_stride(N) * sizeof(float) + (size_t)B * S * sizeof(int);
 }
 
-PWCLO_API int pwclo_knn_sorted(const float* xyz, const float* new_xyz, int B, int N, int S, int K, int sum_order,
-                               const float* warp_qt, float* warped_out, int32_t* idx, float* dist, void* workspace,
-                               size_t workspace_bytes, void* stream) {
-  if (!xyz || !new_xyz || !idx || B < 0 || N <= 0 || S < 0 || K <= 0) return PWCLO_EINVAL;
-  if (K > 32) return PWCLO_EUNSUPPORTED;
-  if (K > N) return PWCLO_EINVAL;
-  if (sum_order != PWCLO_KNN_SUM_XY_Z && sum_order != PWCLO_KNN_SUM_XZ_Y) return PWCLO_EINVAL;
-  if (B == 0 || S == 0) return PWCLO_OK;
-  if (B > 65535) return PWCLO_EUNSUPPORTED;
-  if (N > KNN_MAX_TILE || !workspace || workspace_bytes < pwclo_knn_workspace_bytes(B, N, S) || (uintptr_t)workspace % 16 != 0)
-    return pwclo_knn(xyz, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist, stream);
-  cudaStream_t st = (cudaStream_t)stream;
-  int NP = 1;
+// presort (qorder != nullptr: also the Morton visiting order of the queries) and search, shared by the entry points
+static int knn_presort_launch(const float* xyz, int B, int N, int K, float* workspace, const float* queries, int S, int* qorder,
+                              cudaStream_t st) {
+  int NP = 1, SP = 1;
   while (NP < N) NP <<= 1;
-  const int* qorder_used = nullptr;
-  {
-    int SP = 1;
-    while (SP < S) SP <<= 1;
-    int* qorder = S <= 8192 && getenv("PWCLO_KNN_QORDER") ? reinterpret_cast<int*>((float*)workspace + (size_t)B * knn_ws_stride(N)) : nullptr;
-    const size_t smem = max((size_t)NP * sizeof(u64), qorder ? (size_t)SP * sizeof(unsigned) : (size_t)0);
-    if (smem > 32 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(knn_presort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-    }
-    const char* se = getenv("PWCLO_KNN_STRIPS");
-    knn_presort_kernel<<<B, SORT_THREADS, smem, st>>>(xyz, N, NP, knn_log_strip(NP, K, se ? atoi(se) : 0), (float*)workspace,
-                                                      new_xyz, S, SP, qorder);
-    qorder_used = qorder;
-    int rc = launch_status();
-    if (rc) return rc;
+  while (SP < S) SP <<= 1;
+  const size_t smem = max((size_t)NP * sizeof(u64), qorder ? (size_t)SP * sizeof(unsigned) : (size_t)0);
+  if (smem > 32 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(knn_presort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
   }
+  const char* se = getenv("PWCLO_KNN_STRIPS");
+  knn_presort_kernel<<<B, SORT_THREADS, smem, st>>>(xyz, N, NP, knn_log_strip(NP, K, se ? atoi(se) : 0), workspace, queries, S, SP,
+                                                    qorder);
+  return launch_status();
+}
+
+static int knn_search_launch(const float* workspace, const int* qorder, const float* new_xyz, int B, int N, int S, int K,
+                             int sum_order, const float* warp_qt, float* warped_out, int32_t* idx, float* dist, cudaStream_t st) {
   const size_t smem = knn_ws_stride(N) * sizeof(float) + (size_t)SLAB_WARPS * KNN_BUF * 8 + 128;
   // queries per CTA: amortise the shared-memory fill, keep >= ~3 CTAs per SM in flight overall
   int q_per_cta = SLAB_WARPS;
@@ -926,7 +914,7 @@ PWCLO_API int pwclo_knn_sorted(const float* xyz, const float* new_xyz, int B, in
       cudaError_t e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
-    ks<<<grid, SLAB_WARPS * 32, smem, st>>>((const float*)workspace, new_xyz, N, S, K, q_per_cta, warp_qt, warped_out, idx, dist);
+    ks<<<grid, SLAB_WARPS * 32, smem, st>>>(workspace, new_xyz, N, S, K, q_per_cta, warp_qt, warped_out, idx, dist);
     return launch_status();
   }
   auto kern = sum_order == PWCLO_KNN_SUM_XY_Z ? knn_slab_kernel<0> : knn_slab_kernel<1>;
@@ -942,6 +930,46 @@ PWCLO_API int pwclo_knn_sorted(const float* xyz, const float* new_xyz, int B, in
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k);
     if (e != cudaSuccess) return (int)e;
   }
-  kern<<<grid, warps * 32, smem_k, st>>>((const float*)workspace, qorder_used, new_xyz, N, S, K, q_per_cta, warp_qt, warped_out, idx, dist);
+  kern<<<grid, warps * 32, smem_k, st>>>(workspace, qorder, new_xyz, N, S, K, q_per_cta, warp_qt, warped_out, idx, dist);
   return launch_status();
+}
+
+static int knn_check(const void* a, const void* b, const void* c, int B, int N, int S, int K, int sum_order) {
+  if (!a || !b || !c || B < 0 || N <= 0 || S < 0 || K <= 0) return PWCLO_EINVAL;
+  if (K > 32) return PWCLO_EUNSUPPORTED;
+  if (K > N) return PWCLO_EINVAL;
+  if (sum_order != PWCLO_KNN_SUM_XY_Z && sum_order != PWCLO_KNN_SUM_XZ_Y) return PWCLO_EINVAL;
+  if (B > 65535) return PWCLO_EUNSUPPORTED;
+  return PWCLO_OK;
+}
+
+PWCLO_API int pwclo_knn_sorted(const float* xyz, const float* new_xyz, int B, int N, int S, int K, int sum_order,
+                               const float* warp_qt, float* warped_out, int32_t* idx, float* dist, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (int rc = knn_check(xyz, new_xyz, idx, B, N, S, K, sum_order)) return rc;
+  if (B == 0 || S == 0) return PWCLO_OK;
+  if (N > KNN_MAX_TILE || !workspace || workspace_bytes < pwclo_knn_workspace_bytes(B, N, S) || (uintptr_t)workspace % 16 != 0)
+    return pwclo_knn(xyz, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  int* qorder = S <= 8192 && getenv("PWCLO_KNN_QORDER") ? reinterpret_cast<int*>((float*)workspace + (size_t)B * knn_ws_stride(N)) : nullptr;
+  if (int rc = knn_presort_launch(xyz, B, N, K, (float*)workspace, new_xyz, S, qorder, st)) return rc;
+  return knn_search_launch((const float*)workspace, qorder, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist, st);
+}
+
+PWCLO_API int pwclo_knn_presort(const float* xyz, int B, int N, int K, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!xyz || !workspace || B < 0 || N <= 0 || K <= 0 || K > 32) return PWCLO_EINVAL;
+  if (N > KNN_MAX_TILE || B > 65535) return PWCLO_EUNSUPPORTED;
+  if (workspace_bytes < pwclo_knn_workspace_bytes(B, N, 0) || (uintptr_t)workspace % 16 != 0) return PWCLO_EINVAL;
+  if (B == 0) return PWCLO_OK;
+  return knn_presort_launch(xyz, B, N, K, (float*)workspace, nullptr, 0, nullptr, (cudaStream_t)stream);
+}
+
+PWCLO_API int pwclo_knn_search(const void* workspace, const float* new_xyz, int B, int N, int S, int K, int sum_order,
+                               const float* warp_qt, float* warped_out, int32_t* idx, float* dist, void* stream) {
+  if (int rc = knn_check(workspace, new_xyz, idx, B, N, S, K, sum_order)) return rc;
+  if (N > KNN_MAX_TILE) return PWCLO_EUNSUPPORTED;
+  if ((uintptr_t)workspace % 16 != 0) return PWCLO_EINVAL;
+  if (B == 0 || S == 0) return PWCLO_OK;
+  return knn_search_launch((const float*)workspace, nullptr, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist,
+                           (cudaStream_t)stream);
 }

@@ -184,6 +184,7 @@ class FusedPWCLONet:
         self.L = {k: A.layers(v) for k, v in self.recs.items() if isinstance(v, list)}
         self.LT = {k: A.layers(v) for k, v in self.tc_recs.items()}
         self.use_tc = os.environ.get("PWCLO_TC", "1") != "0"
+        self._sorted = {}
         self.lib = _lib.lib()
         self.launches = 0
         self.verbose_timeline = False
@@ -221,20 +222,33 @@ class FusedPWCLONet:
         self._call("pwclo_gather_rows3", _p(xyz), _p(idx), B, N, idx.shape[1], _p(out))
         return out
 
-    def knn(self, xyz, queries, k, warp_qt=None):
+    def knn(self, xyz, queries, k, warp_qt=None, keep_sorted=False):
+        """Exact kNN of `queries` in `xyz`.  keep_sorted: remember the sorted workspace of these reference clouds
+        (and of the two halves of the batch) for later searches of the same forward (`_sorted`)."""
         B, N, _ = xyz.shape
         S = queries.shape[1]
         idx = self._new(B, S, k, dtype=torch.int32)
         warped = self._new(B, S, 3) if warp_qt is not None else None
+        note = f"[B{B} S{S} N{N} k{k}]" if self.verbose_timeline else ""
+        work = (4 * B * (3 * S + 3 * N + S * k), 0)
         ws_bytes = self.lib.pwclo_knn_workspace_bytes(B, N, S) if _ext.KNN_SORTED and N >= _ext.KNN_SORTED_MIN_N else 0
-        if ws_bytes:
+        hit = self._sorted.get((xyz.data_ptr(), B, N)) if ws_bytes else None
+        if hit is not None:      # these clouds were sorted earlier in this forward: search only
+            self._call("pwclo_knn_search", _p(hit), _p(queries), B, N, S, k, _ext.KNN_SUM_ORDER, _p(warp_qt), _p(warped),
+                       _p(idx), None, note=note, work=work)
+        elif ws_bytes:
             ws = self._new(ws_bytes, dtype=torch.uint8)
             self._call("pwclo_knn_sorted", _p(xyz), _p(queries), B, N, S, k, _ext.KNN_SUM_ORDER, _p(warp_qt), _p(warped),
-                       _p(idx), None, _p(ws), ws_bytes, note=f"[B{B} S{S} N{N} k{k}]" if self.verbose_timeline else "",
-                       work=(4 * B * (3 * S + 3 * N + S * k), 0))
+                       _p(idx), None, _p(ws), ws_bytes, note=note, work=work)
+            if keep_sorted and B % 2 == 0 and not os.environ.get("PWCLO_KNN_QORDER"):
+                rec = self.lib.pwclo_knn_workspace_bytes(1, N, 0)           # bytes per cloud record
+                h = B // 2
+                self._sorted[(xyz.data_ptr(), B, N)] = ws
+                self._sorted[(xyz[:h].data_ptr(), h, N)] = ws[:h * rec]
+                self._sorted[(xyz[h:].data_ptr(), h, N)] = ws[h * rec:B * rec]
         else:
             self._call("pwclo_knn", _p(xyz), _p(queries), B, N, S, k, _ext.KNN_SUM_ORDER, _p(warp_qt), _p(warped), _p(idx),
-                       None, work=(4 * B * (3 * S + 3 * N + S * k), 0))
+                       None, note=note, work=work)
         return (idx, warped) if warp_qt is not None else idx
 
     def set_conv(self, key, xyz, feats, new_xyz, idx):
@@ -321,6 +335,7 @@ class FusedPWCLONet:
         """xyz_f1, xyz_f2: [B,3,N] fp32 CUDA -> (pose_params [B,4,7], embedding_mask_1 [B,64,2048] view,
         new_xyz_f1_1 [B,2048,3])"""
         B = xyz_f1.shape[0]
+        self._sorted = {}          # (data_ptr, clouds, points) -> sorted kNN workspace, valid for this forward only
         with torch.cuda.device(self.device):
             # siamese pyramid: both frames share the weights -> one batch of 2B clouds per level
             xyz = self.to_point_major(torch.cat((xyz_f1, xyz_f2), dim=0).float())
@@ -328,7 +343,7 @@ class FusedPWCLONet:
             for l, (npoint, k) in enumerate(self.LEVELS):
                 fidx = self.fps(xs[-1], npoint)
                 new_xyz = self.gather3(xs[-1], fidx)
-                idx = self.knn(xs[-1], new_xyz, k)
+                idx = self.knn(xs[-1], new_xyz, k, keep_sorted=l >= 1)      # levels 1-3 are searched again below
                 feats = self.set_conv(f"psa_{l + 1}.mlp_module", xs[-1], fs[-1], new_xyz, idx)
                 lvl_idx.append((fidx, idx))
                 xs.append(new_xyz)
@@ -372,4 +387,5 @@ class FusedPWCLONet:
                                   f"pwr{l}.emb": ef, f"pwr{l}.mask": em, f"pwr{l}.qt": qt, f"pwr{l}.idx_q": idx_q,
                                   f"pwr{l}.idx_s": idx_s})
                 emb_prev, mask_prev = ef, em
+        self._sorted = {}
         return pose, mask_prev.permute(0, 2, 1), X1[1]

@@ -123,6 +123,48 @@ def test_knn_sorted_equals_bruteforce(cuda, B, N, S, K):
         assert torch.equal(d1, d0) and torch.equal(i1, i0)
 
 
+def test_knn_presort_search_split(cuda):
+    """pwclo_knn_presort once + pwclo_knn_search per query set (also on a sub-batch of the workspace records)
+    gives the bits of pwclo_knn_sorted; a far-away, rotated query cloud exercises the 3-D pruning bound"""
+    import ctypes
+    from pwclonet_pylidarslam_b200 import _lib
+    L = _lib.lib()
+    B, N = 4, 2048
+    lid = np.stack([synthetic.make_pair(synthetic.SEED_BASE + 80 + i, 8192)["pc2"][:N] for i in range(B)])
+    x = _dev(lid, cuda)
+    c, s_ = np.cos(1.0), np.sin(1.0)
+    R = torch.tensor([[1, 0, 0], [0, c, -s_], [0, s_, c]], dtype=torch.float32, device=cuda)
+    queries = {"subset": x[:, ::2].contiguous(), "rotated": (x[:, ::3] @ R.T + torch.tensor([3.0, -2.0, 5.0], device=cuda)).contiguous()}
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    for K in (6, 32):
+        nbytes = L.pwclo_knn_workspace_bytes(B, N, 0)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=cuda)
+        _lib.check(L.pwclo_knn_presort(vp(x), B, N, K, vp(ws), nbytes, _lib.stream_ptr()), "presort")
+        for name, q in queries.items():
+            S = q.shape[1]
+            want_i, want_d = _ext.knn(x, q, K, return_dist=True)
+            idx = torch.empty(B, S, K, dtype=torch.int32, device=cuda)
+            dist = torch.empty(B, S, K, dtype=torch.float32, device=cuda)
+            _lib.check(L.pwclo_knn_search(vp(ws), vp(q), B, N, S, K, _ext.KNN_SUM_ORDER, None, None, vp(idx), vp(dist),
+                                          _lib.stream_ptr()), "search")
+            assert torch.equal(idx, want_i) and torch.equal(dist, want_d), (K, name)
+            # second half of the batch through its own workspace records
+            rec = L.pwclo_knn_workspace_bytes(1, N, 0)
+            h = B // 2
+            idx2 = torch.empty(h, S, K, dtype=torch.int32, device=cuda)
+            _lib.check(L.pwclo_knn_search(vp(ws[h * rec:]), vp(q[h:].contiguous()), h, N, S, K, _ext.KNN_SUM_ORDER, None, None,
+                                          vp(idx2), None, _lib.stream_ptr()), "search half")
+            assert torch.equal(idx2, want_i[h:]), (K, name)
+            # and against brute force
+            old = _ext.KNN_SORTED
+            try:
+                _ext.KNN_SORTED = False
+                bi, bd = _ext.knn(x, q, K, return_dist=True)
+            finally:
+                _ext.KNN_SORTED = old
+            assert torch.equal(bi, want_i) and torch.equal(bd, want_d), (K, name)
+
+
 def test_knn_query_order_variant(cuda, monkeypatch):
     """optional Morton query ordering + previous-query bound (PWCLO_KNN_QORDER=1): same bits"""
     lid = np.stack([synthetic.make_pair(synthetic.SEED_BASE + 70 + i, 8192)["pc1"] for i in range(2)])
