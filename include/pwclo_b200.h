@@ -200,6 +200,24 @@ int pwclo_gather_rows3(const float *xyz, const int32_t *idx, int B, int N, int M
 int pwclo_transpose(const float *in, int B, int C, int N, int to_point_major, float *out,
                     void *stream);
 
+/* ---- training-side rows ------------------------------------------------ */
+
+/* _PWCLONetLossModule.forward (slam/training/loss_modules.py:424-544, ExponentialWeights :171-196)
+ * and its gradient in one launch.  pred[B,4,7] = (t, q) rows finest level first, gt[B,7] = (t, q),
+ * s[2] = (s_trans, s_rot) of ExponentialWeights (with_exp_weights != 0) or the fixed (trans, rot)
+ * weights.  out[16] = loss | loss_l1..l4 | loss_rot_l1..l4 | loss_trans_l1..l4 | s[0], s[1] | B.
+ * grad_pred[B,4,7] and grad_s[2] (either may be NULL) receive d loss / d pred and d loss / d s. */
+int pwclo_pose_loss(const float *pred, const float *gt, const float *s, int B, int with_exp_weights,
+                    float *out, float *grad_pred, float *grad_s, void *stream);
+
+/* torch.optim.Adam step (the reference's optimiser, slam/training/trainer.py:309-323) over one flat,
+ * 16-byte aligned fp32 arena of n elements: param / exp_avg / exp_avg_sq updated in place from grad.
+ * grad is multiplied by grad_scale first (1/world_size after the gradient all-reduce), then L2 weight
+ * decay is added; `step` counts from 1.  One launch, 28 bytes of HBM traffic per element. */
+int pwclo_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, size_t n,
+                    int step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    float grad_scale, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,3 +84,46 @@ def reference_modules():
     import slam.models.Pointnet2_PyTorch.pointnet2_ops_lib.pointnet2_ops.pointnet2_modules as p2m
     import slam.models.PWCLONet.PWCLO_utils as pwu
     return {"pointnet2_utils": p2u, "pytorch_utils": ptu, "pointnet2_modules": p2m, "PWCLO_utils": pwu}
+
+
+def load_reference_loss(with_exp_weights=True, init_weights=(0.0, -2.5), loss_weights=(1.0, 1.0)):
+    """The UNMODIFIED `_PWCLONetLossModule` (slam/training/loss_modules.py:329-544) on CPU.  Its module
+    imports hydra / pyquaternion / omegaconf.OmegaConf and slam.common.{geometry,optimization,projection},
+    none of which the loss touches: they are stubbed, the class body runs as written."""
+    import dataclasses
+    if not available():
+        raise RuntimeError("reference tree not mounted")
+    _install_stubs(types.ModuleType("pointnet2_ops._ext_stub"))
+    sys.modules["omegaconf"].OmegaConf = type("OmegaConf", (), {"create": staticmethod(lambda x: x)})
+    hy, hc, hcore, hcs = (types.ModuleType(n) for n in ("hydra", "hydra.conf", "hydra.core", "hydra.core.config_store"))
+    hc.dataclass, hc.field, hc.MISSING = dataclasses.dataclass, dataclasses.field, "???"
+
+    class ConfigStore:
+        @staticmethod
+        def instance():
+            return ConfigStore()
+
+        def store(self, **kw):
+            pass
+
+    hcs.ConfigStore = ConfigStore
+    for n, m in (("hydra", hy), ("hydra.conf", hc), ("hydra.core", hcore), ("hydra.core.config_store", hcs)):
+        sys.modules.setdefault(n, m)
+    pq = types.ModuleType("pyquaternion")
+    pq.Quaternion = object
+    sys.modules.setdefault("pyquaternion", pq)
+    sys.modules["slam.common.utils"].check_tensor = lambda *a, **k: None
+    for name, attrs in (("slam.common.geometry", ("compute_normal_map", "projection_map_to_points")),
+                        ("slam.common.optimization", ("_LS_SCHEME", "_WLSScheme", "PointToPlaneCost")),
+                        ("slam.common.projection", ("Projector",))):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            for a in attrs:
+                setattr(m, a, object)
+            sys.modules[name] = m
+    import importlib
+    lm = importlib.import_module("slam.training.loss_modules")
+    cfg = DictConfig(mode="supervised", loss_degrees=False, loss_weights=list(loss_weights),
+                     with_exp_weights=with_exp_weights, init_weights=list(init_weights), loss_option="l2_norm",
+                     nb_levels=4, device="cpu", scalar_last=False)
+    return lm._PWCLONetLossModule(cfg, sys.modules["slam.common.pose"].Pose("quaternions"))

@@ -1,0 +1,178 @@
+// train_ops.cu -- training-side rows: the PWCLO-Net loss with its gradient in ONE launch, and the
+// Adam update of the flat parameter arena in ONE launch.
+//
+// Reference: _PWCLONetLossModule.forward (slam/training/loss_modules.py:424-544) with
+// ExponentialWeights.forward (:171-196).  The reference builds the value out of ~120 element-wise
+// torch launches on [B,4,7] tensors and autograd replays as many for the gradient; here one CTA
+// evaluates the four per-level rotation / translation terms, the weighted total, d loss / d pred and
+// d loss / d s.  The problem is tiny (B x 28 floats): the kernel is launch-latency bound by design.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pwclo {
+
+constexpr int kLossThreads = 256;
+constexpr int kLossTerms = 8;   // rot_l, trans_l for the 4 levels
+
+// out[16]: 0 loss | 1..4 loss_l1..l4 | 5..8 loss_rot_l1..l4 | 9..12 loss_trans_l1..l4 | 13,14 s (or weights) | 15 B
+__global__ void __launch_bounds__(kLossThreads)
+pose_loss_kernel(const float* __restrict__ pred, const float* __restrict__ gt, const float* __restrict__ s, int B,
+                 int with_exp, float* __restrict__ out, float* __restrict__ grad_pred, float* __restrict__ grad_s) {
+  __shared__ float red[kLossTerms][kLossThreads / 32];
+  const float s_t = s[0], s_q = s[1];
+  // d loss / d (level term): level weights 0.2,0.4,0.8,1.6 for rows 0..3 (row 0 = finest level,
+  // loss_modules.py:531), times exp(-s) (ExponentialWeights) or the fixed weight (:519-522)
+  const float wt = with_exp ? expf(-s_t) : s_t;
+  const float wq = with_exp ? expf(-s_q) : s_q;
+  const float invB = 1.f / (float)B, inv3B = 1.f / (3.f * (float)B);
+
+  float acc[kLossTerms];
+#pragma unroll
+  for (int i = 0; i < kLossTerms; ++i) acc[i] = 0.f;
+
+  for (int item = threadIdx.x; item < B * 4; item += kLossThreads) {
+    const int b = item >> 2, l = item & 3;
+    const float* p = pred + (size_t)item * 7;
+    const float* g = gt + (size_t)b * 7;
+    const float lw = 0.2f * (float)(1 << l);
+    // translation: mean over (b, c) of sqrt((t-g)^2 + 1e-10)            (:382-384)
+    float tsum = 0.f, gtr[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float d = p[c] - g[c];
+      const float r = sqrtf(d * d + 1e-10f);
+      tsum += r;
+      gtr[c] = lw * wt * inv3B * d / r;
+    }
+    // rotation: q/(sqrt(sum q^2 + 1e-10) + 1e-10), then mean over b of sqrt(sum (qn-g)^2 + 1e-10)   (:370-373, :388-391)
+    const float q0 = p[3], q1 = p[4], q2 = p[5], q3 = p[6];
+    const float r = sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3 + 1e-10f);
+    const float n = r + 1e-10f;
+    const float e0 = q0 / n - g[3], e1 = q1 / n - g[4], e2 = q2 / n - g[5], e3 = q3 / n - g[6];
+    const float d = sqrtf(e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3 + 1e-10f);
+    if (grad_pred) {
+      float* gp = grad_pred + (size_t)item * 7;
+      gp[0] = gtr[0]; gp[1] = gtr[1]; gp[2] = gtr[2];
+      // d d / d qn_i = e_i / d ; d qn_i / d q_j = delta_ij / n - q_i q_j / (n^2 r)
+      const float k = lw * wq * invB / d;
+      const float h0 = k * e0, h1 = k * e1, h2 = k * e2, h3 = k * e3;
+      const float hq = (h0 * q0 + h1 * q1 + h2 * q2 + h3 * q3) / (n * n * r);
+      gp[3] = h0 / n - q0 * hq;
+      gp[4] = h1 / n - q1 * hq;
+      gp[5] = h2 / n - q2 * hq;
+      gp[6] = h3 / n - q3 * hq;
+    }
+    // branch-free scatter into the per-level accumulators
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[j] += (l == j) ? d : 0.f;
+      acc[4 + j] += (l == j) ? tsum : 0.f;
+    }
+  }
+  // block reduction in a fixed order: shuffle tree inside a warp, then warp 0 adds the 8 partials
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kLossTerms; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(PWCLO_FULL_MASK, v, o);
+    if (lane == 0) red[i][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float rot[4], tr[4], lvl[4], total = 0.f, ds_t = 0.f, ds_q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = 0.f, b = 0.f;
+      for (int w = 0; w < kLossThreads / 32; ++w) { a += red[i][w]; b += red[4 + i][w]; }
+      rot[i] = a * invB;
+      tr[i] = b * inv3B;
+      const float lw = 0.2f * (float)(1 << i);
+      lvl[i] = with_exp ? (tr[i] * wt + s_t) + (rot[i] * wq + s_q) : tr[i] * wt + rot[i] * wq;
+      ds_t += lw * (1.f - tr[i] * wt);
+      ds_q += lw * (1.f - rot[i] * wq);
+    }
+    // 1.6*L4 + 0.8*L3 + 0.4*L2 + 0.2*L1, added in the reference's order (:531)
+    total = 1.6f * lvl[3] + 0.8f * lvl[2] + 0.4f * lvl[1] + 0.2f * lvl[0];
+    out[0] = total;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { out[1 + i] = lvl[i]; out[5 + i] = rot[i]; out[9 + i] = tr[i]; }
+    out[13] = s_t; out[14] = s_q; out[15] = (float)B;
+    if (grad_s) {
+      if (with_exp) { grad_s[0] = ds_t; grad_s[1] = ds_q; }
+      else {
+        // fixed weights: d loss / d weight = sum_l lw * term_l (not a trained quantity in the reference)
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < 4; ++i) { a += 0.2f * (float)(1 << i) * tr[i]; b += 0.2f * (float)(1 << i) * rot[i]; }
+        grad_s[0] = a; grad_s[1] = b;
+      }
+    }
+  }
+}
+
+// torch.optim.Adam (the optimiser the reference builds, slam/training/trainer.py:309-323; betas (0.9, 0.999),
+// L2 weight decay added to the gradient) over ONE flat fp32 arena holding every trainable parameter:
+// 16 B read + 12 B written per element, float4-vectorised, grid-stride.  Operation order follows
+// torch's single-tensor implementation so results agree to fp32 rounding:
+//   g += wd*p ; m = lerp(m, g, 1-b1) ; v = b2*v + (1-b2)*g*g ; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float lr_over_bc1, float b1, float b2,
+                                         float eps, float wd, float sqrt_bc2, float gscale) {
+  g *= gscale;
+  g = fmaf(wd, p, g);
+  m = fmaf(1.f - b1, g - m, m);
+  v = fmaf(1.f - b2, g * g, b2 * v);
+  const float denom = sqrtf(v) / sqrt_bc2 + eps;
+  p = fmaf(-lr_over_bc1, m / denom, p);
+}
+
+__global__ void __launch_bounds__(256)
+adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 size_t n, float lr_over_bc1, float b1, float b2, float eps, float wd, float sqrt_bc2, float gscale) {
+  const size_t n4 = n >> 2;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adam_one(pp.x, gg.x, mm.x, vv.x, lr_over_bc1, b1, b2, eps, wd, sqrt_bc2, gscale);
+    adam_one(pp.y, gg.y, mm.y, vv.y, lr_over_bc1, b1, b2, eps, wd, sqrt_bc2, gscale);
+    adam_one(pp.z, gg.z, mm.z, vv.z, lr_over_bc1, b1, b2, eps, wd, sqrt_bc2, gscale);
+    adam_one(pp.w, gg.w, mm.w, vv.w, lr_over_bc1, b1, b2, eps, wd, sqrt_bc2, gscale);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail (n not a multiple of 4)
+  for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    adam_one(p[i], g[i], m[i], v[i], lr_over_bc1, b1, b2, eps, wd, sqrt_bc2, gscale);
+}
+
+}  // namespace pwclo
+
+PWCLO_API int pwclo_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int step,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                              void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || step < 1) return PWCLO_EINVAL;
+  if (n == 0) return PWCLO_OK;
+  if ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) != 0) return PWCLO_EINVAL;
+  // bias corrections in double on the host, as torch does with python floats
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float lr_over_bc1 = (float)((double)lr / bc1), sqrt_bc2 = (float)sqrt(bc2);
+  const size_t n4 = (n + 3) / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  const int cap = pwclo::kNumSM * 8;
+  if (blocks > cap) blocks = cap;
+  pwclo::adam_step_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr_over_bc1, beta1,
+                                                                    beta2, eps, weight_decay, sqrt_bc2, grad_scale);
+  return pwclo::launch_status();
+}
+
+PWCLO_API int pwclo_pose_loss(const float* pred, const float* gt, const float* s, int B, int with_exp_weights, float* out,
+                              float* grad_pred, float* grad_s, void* stream) {
+  if (!pred || !gt || !s || !out || B <= 0) return PWCLO_EINVAL;
+  pwclo::pose_loss_kernel<<<1, pwclo::kLossThreads, 0, (cudaStream_t)stream>>>(pred, gt, s, B, with_exp_weights ? 1 : 0, out,
+                                                                               grad_pred, grad_s);
+  return pwclo::launch_status();
+}

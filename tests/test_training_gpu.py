@@ -47,3 +47,117 @@ def test_train_step_forward_backward(cuda):
     assert total > 0
     # level-1 set conv only has weight gradients (its input is raw xyz): they must be non-zero
     assert float(net.psa_1.mlp_module.layer0.conv.weight.grad.abs().sum()) > 0
+
+
+# ---- training-side rows (F15 / N1): loss + gradient kernel, flat Adam, trainer, checkpoints -------------
+def _loss_cases():
+    import os
+    g = dict(np.load(os.path.join(C.GOLD_DIR, "loss_kat.npz")))
+    for i in range(int(g["n_cases"])):
+        yield i, {k[len(f"c{i}_"):]: v for k, v in g.items() if k.startswith(f"c{i}_")}
+
+
+def test_pose_loss_kernel_matches_reference_golden(cuda):
+    """value and gradient of pwclo_pose_loss against the unmodified reference loss module (fixture made by
+    oracle/make_golden_train.py).  fp32 with a different summation order than torch.mean: 2e-6 relative
+    on the terms, 1e-5 relative (to the largest gradient entry) on the gradients."""
+    from pwclonet_pylidarslam_b200 import training as T
+    for i, c in _loss_cases():
+        with_exp = bool(c["with_exp"])
+        cfg = T.PWCLONetLossConfig(with_exp_weights=with_exp, init_weights=[float(v) for v in c["s"]],
+                                   loss_weights=[float(v) for v in c["s"]])
+        mod = T._PWCLONetLossModule(cfg).to(cuda)
+        p = torch.tensor(c["pred"], device=cuda, requires_grad=True)
+        loss, log = mod(p, torch.tensor(c["gt"], device=cuda))
+        loss.backward()
+        keys = (["loss"] + [f"loss_l{j}" for j in range(1, 5)] + [f"loss_rot_l{j}" for j in range(1, 5)]
+                + [f"loss_trans_l{j}" for j in range(1, 5)])
+        got = np.array([float(log[k]) for k in keys], np.float32)
+        np.testing.assert_allclose(got, c["terms"], rtol=2e-6, atol=1e-7, err_msg=f"case {i}")
+        gp = p.grad.cpu().numpy()
+        assert np.abs(gp - c["grad_pred"]).max() <= 1e-5 * np.abs(c["grad_pred"]).max() + 1e-9, f"case {i}"
+        if with_exp:
+            gs = mod.exp_weighting.s_param.grad.cpu().numpy()
+            np.testing.assert_allclose(gs, c["grad_s"], rtol=1e-5, atol=1e-6, err_msg=f"case {i}")
+
+
+def test_pose_loss_kernel_matches_oracle_large_batch(cuda):
+    from oracle import train_port
+    from pwclonet_pylidarslam_b200 import training as T
+    rng = np.random.default_rng(11)
+    pred = rng.standard_normal((1000, 4, 7)).astype(np.float32)
+    gt = rng.standard_normal((1000, 7)).astype(np.float32)
+    o = train_port.pose_loss(pred, gt, [0.1, -2.0])
+    mod = T._PWCLONetLossModule(T.PWCLONetLossConfig(init_weights=[0.1, -2.0])).to(cuda)
+    p = torch.tensor(pred, device=cuda, requires_grad=True)
+    loss, _ = mod(p, torch.tensor(gt, device=cuda))
+    (2.0 * loss).backward()                          # upstream gradient is honoured
+    assert abs(float(loss) - o["loss"]) <= 2e-6 * abs(o["loss"])
+    assert np.abs(p.grad.cpu().numpy() - 2.0 * o["grad_pred"]).max() <= 1e-5 * np.abs(2.0 * o["grad_pred"]).max()
+
+
+def test_flat_adam_matches_torch_adam(cuda):
+    """pwclo_adam_step over the flat arena == torch.optim.Adam on the same tensors (fp32 rounding only)"""
+    from pwclonet_pylidarslam_b200 import training as T
+    torch.manual_seed(0)
+    a = torch.nn.Sequential(torch.nn.Linear(33, 65), torch.nn.ReLU(), torch.nn.Linear(65, 7)).to(cuda)
+    b = torch.nn.Sequential(torch.nn.Linear(33, 65), torch.nn.ReLU(), torch.nn.Linear(65, 7)).to(cuda)
+    b.load_state_dict(a.state_dict())
+    arena = T.FlatArena([a])
+    ours = T.FlatAdam(arena, lr=1e-3, weight_decay=1e-3)
+    ref = torch.optim.Adam(b.parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-3, foreach=False)
+    for step in range(6):
+        x = torch.randn(16, 33, device=cuda)
+        ours.zero_grad()
+        ref.zero_grad()
+        a(x).square().mean().backward()
+        b(x).square().mean().backward()
+        ours.step()
+        ref.step()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-6)
+    # the optimiser state moves to torch.optim.Adam and back (checkpoint compatibility, trainer.py:884)
+    ref2 = torch.optim.Adam(b.parameters(), lr=1e-3, weight_decay=1e-3)
+    ref2.load_state_dict(ours.state_dict())
+    assert int(ref2.state_dict()["state"][0]["step"]) == 6
+    again = T.FlatAdam(T.FlatArena([b]), lr=5e-4)
+    again.load_state_dict(ref.state_dict())
+    assert again.steps == 6 and abs(again.lr - 1e-3) < 1e-12
+    torch.testing.assert_close(again.exp_avg, ours.exp_avg, rtol=1e-4, atol=1e-7)
+
+
+def test_trainer_step_and_checkpoint_roundtrip(cuda, tmp_path):
+    """one PWCLONetTrainer: a few steps on a fixed batch reduce the loss; checkpoint has the reference's
+    keys (trainer.py:882-907) and restores parameters, optimiser state and schedules exactly."""
+    from pwclonet_pylidarslam_b200 import synthetic as syn
+    from pwclonet_pylidarslam_b200 import training as T
+    torch.manual_seed(0)
+    cfg = T.PWCLONetTrainerConfig(num_points=4096, num_epochs=10, optimizer_weight_decay=0.0)
+    tr = T.PWCLONetTrainer(cfg)
+    assert tr.arena.count == 775070                        # SURVEY 8e: 775 068 + 2
+    x1, x2, gt = syn.make_batch(700, 2, 4096)
+    batch = [torch.from_numpy(np.ascontiguousarray(x1.transpose(0, 2, 1))).to(cuda),
+             torch.from_numpy(np.ascontiguousarray(x2.transpose(0, 2, 1))).to(cuda),
+             torch.from_numpy(gt[:, 3:]).to(cuda), torch.from_numpy(gt[:, :3]).to(cuda)]
+    losses = []
+    for _ in range(6):
+        loss, log, pred = tr.train_step(batch)
+        losses.append(float(loss))
+        assert pred.shape == (2, 4, 7)
+    assert all(np.isfinite(losses)) and min(losses[1:]) < losses[0], losses
+    tr.end_epoch()
+    ck = str(tmp_path / "0.ckp")
+    tr.save_checkpoint(ck)
+    sd = torch.load(ck, weights_only=False)
+    assert {"optimizer", "loss_module", "prediction_module", "num_train_epochs", "train_iter", "eval_iter", "best"} <= set(sd)
+    assert len(sd["prediction_module"]) == 510 and all(k.startswith("pwclonet.") for k in sd["prediction_module"])
+    tr2 = T.PWCLONetTrainer(cfg)
+    tr2.load_checkpoint(ck)
+    assert torch.equal(tr2.arena.param, tr.arena.param) and torch.equal(tr2._optimizer.exp_avg_sq, tr._optimizer.exp_avg_sq)
+    assert tr2._optimizer.steps == 6 and tr2.num_epochs == 1 and tr2._optimizer.lr == tr._optimizer.lr
+    # both continue identically (dropout seeds aligned)
+    torch.manual_seed(5)
+    l1, _, _ = tr.train_step(batch)
+    torch.manual_seed(5)
+    l2, _, _ = tr2.train_step(batch)
+    assert abs(float(l1) - float(l2)) <= 1e-5 * abs(float(l1))
