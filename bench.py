@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--pairs-per-gpu", type=int, default=64)
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs generated per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="train = BASELINE config 5: forward+backward+all-reduce+Adam, 8 pairs per GPU x 16384 points")
+    ap.add_argument("--train-points", type=int, default=16384)
+    ap.add_argument("--train-pairs-per-gpu", type=int, default=8)
     return ap.parse_args()
 
 
@@ -55,6 +59,17 @@ def peaks():
         return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured"
     except Exception:
         return 6650.0, 1590.0, "fallback"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of each kernel family, from the committed ncu capture (profiles/*_traffic.json,
+    written by tools/traffic_from_ncu.py); bench.py never runs under a profiler itself."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return {}, None
+    d = json.load(open(files[-1]))
+    return d.get("families", {}), os.path.relpath(files[-1], ROOT)
 
 
 def _gen_pair(seed):
@@ -172,6 +187,115 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args, world, rank, local):
+    """BASELINE config 5: training step = zero_grad, forward (train-mode BN, dropout), loss,
+    backward, ONE NCCL all-reduce of the flat gradient arena, one-launch Adam; `--train-pairs-per-gpu`
+    pairs of `--train-points` points per GPU (weak scaling).  Reports pairs/s and the all-reduce time."""
+    global N_POINTS
+    N_POINTS = args.train_points
+    P = args.train_pairs_per_gpu
+    h1, h2 = make_inputs(rank, P, P)
+    import torch.distributed as dist
+    from pwclonet_pylidarslam_b200 import _lib
+    from pwclonet_pylidarslam_b200 import training as T
+    _lib.lib()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    tr = T.PWCLONetTrainer(T.PWCLONetTrainerConfig(num_points=N_POINTS, device=str(dev), batch_size=P))
+    rng = np.random.default_rng(7 + rank)
+    q = rng.standard_normal((P, 4)).astype(np.float32) * 0.02 + np.array([1, 0, 0, 0], np.float32)
+    q /= np.linalg.norm(q, axis=-1, keepdims=True)
+    t = (rng.standard_normal((P, 3)) * np.array([0.05, 0.02, 0.3]) + np.array([0, 0, 1.0])).astype(np.float32)
+    pin = [torch.from_numpy(np.ascontiguousarray(h1.transpose(0, 2, 1))).pin_memory(),
+           torch.from_numpy(np.ascontiguousarray(h2.transpose(0, 2, 1))).pin_memory(),
+           torch.from_numpy(q).pin_memory(), torch.from_numpy(t).pin_memory()]
+    res = [b.to(dev) for b in pin]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return tr.train_step(res)[0]
+
+    def step_e2e():
+        return tr.train_step([b.to(dev, non_blocking=True) for b in pin])[0].cpu()
+
+    def timed(fn, steps):
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn()
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs), out
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ms_total, loss = timed(step_resident, args.steps)
+    barrier()
+    sampler.stop_flag = True
+    step_e2e()
+    barrier()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    barrier()
+    # the collective and the optimiser alone (CUDA events on the launching stream)
+    def alone(fn, n=20):
+        fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / n
+    ms_ar = alone(lambda: T.all_reduce_gradients(tr.arena))
+    ms_adam = alone(lambda: tr._optimizer.step(1.0))
+    tt = torch.tensor([ms_total, ms_e2e, ms_ar, ms_adam], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e, ms_ar, ms_adam = [float(v) for v in tt]
+    if rank == 0:
+        hbm_peak, _, peak_kind = peaks()
+        adam_bytes = tr.arena.numel * 28
+        ach = adam_bytes / (ms_adam * 1e-3) / 1e9
+        line = {"metric": f"PWCLO-Net training frame-pairs/s ({N_POINTS} pts, fwd+bwd+allreduce+Adam)",
+                "value": world * P * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"BASELINE config 5: training forward+backward, {P} frame pairs per GPU x {N_POINTS} points, "
+                                       "train-mode BatchNorm + dropout, one all-reduce of the flat gradient arena, Adam",
+                           "pairs_per_gpu": P, "points": N_POINTS, "l2": "flushed between timed steps (256 MB write)",
+                           "parallelism": f"data parallel x{world}, one NCCL all-reduce of {tr.arena.numel} fp32 per step",
+                           "note": "sampling / neighbour / grouping ops and the loss on the sm_100a kernels; 1x1 convs, BN and "
+                                   "their backward by torch (fused-layer backward is not built)"},
+                "e2e": {"value": world * P * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": int(sum(b.numel() * 4 for b in pin)), "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "allreduce_ms": ms_ar, "allreduce_bytes": tr.arena.numel * 4, "adam_ms": ms_adam,
+                "loss": float(loss), "clocks": sampler.summary(),
+                "roofline": {"bound": "hbm", "kernel": "pwclo_adam_step", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": ach / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                             "note": "the one training kernel that is purely HBM streaming (28 B per parameter); 3.1 MB "
+                                     "arena stays in L2 between steps, so this is an L2-resident figure"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -184,6 +308,9 @@ def main():
                                    "29533", os.path.abspath(__file__)] + sys.argv[1:])
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.mode == "train":
+        run_train(args, world, rank, local)
         return
 
     P = args.pairs_per_gpu
@@ -277,20 +404,31 @@ def main():
         top_ms, top_name, top_n = shares[0]
         mlp_kernels = {k for k in per_kernel if any(t in k for t in ("set_conv", "pointwise_mlp", "cost_volume"))}
 
+        traffic_tab, traffic_src = ncu_traffic()
+
+        def traffic_of(name):
+            fam = "pwclo_knn" if name.startswith("pwclo_knn") else name
+            t = traffic_tab.get(fam)
+            return (t["dram_bytes_per_launch"], traffic_src) if t else (None, None)
+
         def roof_of(name):
             """achieved = algorithmic bytes (or MLP flops) of all launches of this kernel / their summed duration"""
             ms = sum(per_kernel[name])
             by, fl = per_work[name]
+            traffic, tsrc = traffic_of(name)
             if name in mlp_kernels:
                 ach = fl / (ms * 1e-3) / 1e12
                 return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
-                        "frac": ach / tf_peak, "traffic": None, "peak_kind": peak_kind + " (cuBLAS bf16 sustained)",
+                        "frac": ach / tf_peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)",
+                        "traffic_source": tsrc, "peak_kind": peak_kind + " (cuBLAS bf16 sustained)",
                         "ms_per_step": ms, "launches_per_step": len(per_kernel[name]),
                         "note": "fp32-accurate split product (tf32 + 2 bf16 correction MMAs: 8 tcgen05.mma per 32 inputs); "
                                 "flops counted once; the kernels are bound by TMEM operand/accumulator reads, see DESIGN.md"}
             ach = by / (ms * 1e-3) / 1e9
             return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": None, "peak_kind": peak_kind, "ms_per_step": ms, "launches_per_step": len(per_kernel[name]),
+                    "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)", "traffic_source": tsrc,
+                    "algorithmic_bytes_per_launch": by / max(1, len(per_kernel[name])),
+                    "peak_kind": peak_kind, "ms_per_step": ms, "launches_per_step": len(per_kernel[name]),
                     "note": "algorithmic bytes of SURVEY 8d; this kernel is latency/ALU bound, not HBM bound"}
 
         roof = roof_of(top_name)

@@ -1,0 +1,63 @@
+"""GPU input pipeline: raw KITTI scans -> the [B,N,3] float32 clouds PWCLO-Net consumes.
+
+Replaces, per frame, the host numpy code of slam/dataset/kitti_odometry_dataset.py:375-397 (`Tr`
+transform in float64) and `filter_pcd` :149-172 (ground / range crop + `npoints` random survivors), and
+the optional augmentation transform :404-446, by ONE launch of `pwclo_prepare_scans` over a packed batch
+of scans.  There is no CPU path: tensors must live on the GPU.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def pack_scans(scans, pin=True):
+    """list of float32 [n_i,4] arrays (what np.fromfile(bin, float32).reshape(-1, 4) returns) ->
+    (packed float32 [sum n_i, 4] host tensor, int64 [len+1] offsets, max n_i).  For a frame PAIR the reference
+    truncates both scans to the shorter one first (kitti_odometry_dataset.py:378-384): see `pack_pairs`."""
+    sizes = [int(s.shape[0]) for s in scans]
+    off = np.zeros(len(scans) + 1, np.int64)
+    off[1:] = np.cumsum(sizes)
+    buf = torch.empty((int(off[-1]), 4), dtype=torch.float32)
+    if pin and torch.cuda.is_available():
+        buf = buf.pin_memory()
+    for s, o in zip(scans, off[:-1]):
+        buf[o:o + s.shape[0]] = torch.from_numpy(np.ascontiguousarray(s, np.float32).reshape(-1, 4))
+    return buf, torch.from_numpy(off), max(sizes) if sizes else 0
+
+
+def pack_pairs(scans1, scans2, pin=True):
+    """frame pairs: both scans of a pair are cut to the shorter length (reference :378-384); returns the
+    packing of [pair0.scan1, pair0.scan2, pair1.scan1, ...]"""
+    seq = []
+    for a, b in zip(scans1, scans2):
+        n = min(a.shape[0], b.shape[0])
+        seq += [a[:n], b[:n]]
+    return pack_scans(seq, pin)
+
+
+def prepare_scans(raw, offsets, Tr, npoints, seed, post=None, max_points=None, return_index=False):
+    """raw float32 [total,4] CUDA, offsets int64 [S+1] CUDA, Tr float64 [3,4] (or [S,3,4]) CUDA ->
+    clouds float32 [S,npoints,3] (+ int32 [S,npoints] source rows, int32 [S] survivors)."""
+    for t, name, dt in ((raw, "raw", torch.float32), (offsets, "offsets", torch.int64), (Tr, "Tr", torch.float64)):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dt and t.is_contiguous()):
+            raise RuntimeError(f"{name} must be a contiguous {dt} CUDA tensor (there is no CPU path)")
+    S = offsets.numel() - 1
+    per_scan = Tr.dim() == 3
+    if Tr.numel() != (12 * S if per_scan else 12):
+        raise RuntimeError("Tr must be [3,4] or [S,3,4]")
+    if post is not None and not (post.is_cuda and post.dtype == torch.float64 and post.is_contiguous() and post.numel() == 12 * S):
+        raise RuntimeError("post must be a contiguous float64 CUDA tensor [S,3,4]")
+    if max_points is None:
+        max_points = int((offsets[1:] - offsets[:-1]).max()) if S else 1      # one small D2H read; pass it to avoid
+    out = torch.empty((S, npoints, 3), dtype=torch.float32, device=raw.device)
+    idx = torch.empty((S, npoints), dtype=torch.int32, device=raw.device)
+    surv = torch.empty((S,), dtype=torch.int32, device=raw.device)
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    with torch.cuda.device(raw.device):
+        _lib.check(_lib.lib().pwclo_prepare_scans(p(raw), p(offsets), S, int(max_points), p(Tr), 1 if per_scan else 0, p(post),
+                                                  ctypes.c_ulonglong(int(seed) & (2 ** 64 - 1)), int(npoints), p(out), p(idx),
+                                                  p(surv), _lib.stream_ptr()), "prepare_scans")
+    return (out, idx, surv) if return_index else out

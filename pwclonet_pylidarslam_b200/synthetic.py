@@ -144,3 +144,26 @@ def make_state_dict(shapes, seed=1):
         else:
             raise KeyError(f"unexpected parameter name {name}")
     return out
+
+
+# KITTI odometry sequence-00 style velodyne -> camera calibration (rows 0..2 of the 4x4 `Tr`,
+# slam/dataset/kitti_odometry_dataset.py:353-355): x_cam = -y_velo, y_cam = -z_velo, z_cam = x_velo up to a
+# sub-degree rotation and a few centimetres of lever arm.
+KITTI_TR = np.array([[4.276802385584e-04, -9.999672484946e-01, -8.084491683471e-03, -1.198459927713e-02],
+                     [-7.210626507497e-03, 8.081198471645e-03, -9.999413164504e-01, -5.403984729748e-02],
+                     [9.999738645903e-01, 4.859485810390e-04, -7.206933692422e-03, -2.921968648686e-01]], np.float64)
+
+
+def make_raw_scan(seed):
+    """A synthetic KITTI `.bin` payload: float32 [n,4] = (x, y, z, reflectance) in the VELODYNE frame, i.e. what
+    `np.fromfile(..., float32).reshape(-1, 4)` returns (kitti_odometry_dataset.py:375-376), such that
+    KITTI_TR maps it to the camera-style frame of `make_pair`.  All ~10^5 returns of one revolution, unfiltered,
+    in beam-major firing order."""
+    rng = np.random.Generator(np.random.PCG64([int(seed), 77]))
+    lo, hi = _scene(rng)
+    cam = _scan(lo, hi, np.zeros(3), np.eye(3), rng)
+    T = np.vstack([KITTI_TR, [0.0, 0.0, 0.0, 1.0]])
+    Ti = np.linalg.inv(T)
+    velo = cam @ Ti[:3, :3].T + Ti[:3, 3]
+    refl = rng.uniform(0.0, 1.0, size=(velo.shape[0], 1))
+    return np.ascontiguousarray(np.concatenate([velo, refl], axis=1), np.float32)

@@ -59,8 +59,11 @@ def _loss_cases():
 
 def test_pose_loss_kernel_matches_reference_golden(cuda):
     """value and gradient of pwclo_pose_loss against the unmodified reference loss module (fixture made by
-    oracle/make_golden_train.py).  fp32 with a different summation order than torch.mean: 2e-6 relative
-    on the terms, 1e-5 relative (to the largest gradient entry) on the gradients."""
+    oracle/make_golden_train.py).  fp32 with a different summation order than torch.sum / torch.mean: 2e-6
+    relative on the terms; gradients 1e-5 relative to the largest entry for O(1) errors, 1e-4 for the "near"
+    cases (pose errors ~1e-3, as for a trained network): there q/|q| - q_gt cancels three digits, so a 1-ulp
+    difference in |q| (summation order of four squares) moves the gradient by ~5e-5 relative in ANY fp32
+    evaluation, the reference's included."""
     from pwclonet_pylidarslam_b200 import training as T
     for i, c in _loss_cases():
         with_exp = bool(c["with_exp"])
@@ -75,7 +78,9 @@ def test_pose_loss_kernel_matches_reference_golden(cuda):
         got = np.array([float(log[k]) for k in keys], np.float32)
         np.testing.assert_allclose(got, c["terms"], rtol=2e-6, atol=1e-7, err_msg=f"case {i}")
         gp = p.grad.cpu().numpy()
-        assert np.abs(gp - c["grad_pred"]).max() <= 1e-5 * np.abs(c["grad_pred"]).max() + 1e-9, f"case {i}"
+        near = float(np.abs(c["pred"] - c["gt"][:, None, :]).max()) < 0.05
+        tol = 1e-4 if near else 1e-5
+        assert np.abs(gp - c["grad_pred"]).max() <= tol * np.abs(c["grad_pred"]).max() + 1e-9, f"case {i}"
         if with_exp:
             gs = mod.exp_weighting.s_param.grad.cpu().numpy()
             np.testing.assert_allclose(gs, c["grad_s"], rtol=1e-5, atol=1e-6, err_msg=f"case {i}")

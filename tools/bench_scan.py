@@ -1,0 +1,55 @@
+"""Roofline of pwclo_prepare_scans (N3): a batch of synthetic KITTI scans, CUDA-event timed, against the
+algorithmic bytes (16 B per scan point read once + 12 B per output point) and the measured HBM peak; the
+reference's numpy path (oracle/scan_port.reference_transform_and_mask + np.random.choice) timed beside it.
+usage: python tools/bench_scan.py [nscan]"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from pwclonet_pylidarslam_b200 import scan_input, synthetic as syn  # noqa: E402
+
+nscan = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+dev = torch.device("cuda:0")
+base = [syn.make_raw_scan(100 + i) for i in range(8)]
+scans = [base[i % 8] for i in range(nscan)]
+buf, off, mx = scan_input.pack_scans(scans)
+raw, offd, Tr = buf.to(dev), off.to(dev), torch.from_numpy(syn.KITTI_TR.copy()).to(dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for _ in range(3):
+    scan_input.prepare_scans(raw, offd, Tr, 8192, 1, max_points=mx)
+times = []
+for it in range(10):
+    flush.zero_()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    scan_input.prepare_scans(raw, offd, Tr, 8192, it, max_points=mx)
+    e.record()
+    torch.cuda.synchronize()
+    times.append(s.elapsed_time(e))
+ms = float(np.median(times))
+total = int(off[-1])
+alg = total * 16 + nscan * 8192 * 12
+try:
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    peak = 6650.0
+# the reference's host path on one scan (numpy, this box)
+from oracle import scan_port as S  # noqa: E402  (checker / CPU baseline only)
+Tr4 = np.vstack([syn.KITTI_TR, [0, 0, 0, 1.0]])
+t0 = time.perf_counter()
+for i in range(8):
+    pts, mask = S.reference_transform_and_mask(base[i], Tr4)
+    idx = np.where(mask)[0]
+    sel = np.random.choice(idx, 8192, replace=False)
+    out = pts[sel].astype(np.float32)
+cpu_ms = (time.perf_counter() - t0) / 8 * 1e3
+print(json.dumps({"kernel": "pwclo_prepare_scans", "scans": nscan, "points": total, "ms": ms, "ms_all": times,
+                  "scans_per_s": nscan / (ms * 1e-3), "algorithmic_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9,
+                  "peak_gbs": peak, "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                  "cpu_reference_ms_per_scan": cpu_ms, "cpu_scans_per_s_1core": 1e3 / cpu_ms}))
