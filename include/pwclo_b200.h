@@ -238,6 +238,18 @@ int pwclo_prepare_scans(const float *raw, const long long *offsets, int nscan, i
                         unsigned long long seed, int npoints, float *out, int32_t *sel_idx,
                         int32_t *survivors, void *stream);
 
+/* ---- pose post-processing ------------------------------------------------ */
+
+/* pose_params rows (t[3], q[4] scalar first; `row_stride` floats apart, 28 for the finest-level row of
+ * [B,4,7]) -> float64 4x4 matrices [B,16]: quat2mat of train.py:762-796 (fp32, op for op) with t in the
+ * last column; invert != 0 returns the inverse as train.py:885 does (np.linalg.inv). */
+int pwclo_pose_to_matrix(const float *pose_params, int B, int row_stride, int invert, double *out,
+                         void *stream);
+/* KITTI360_TRANSFORMATIONS.convert_to_absolute, dict branch (slam/common/kitti360_utils.py:424-427):
+ * abs_f = inv(rel_f @ inv(abs_{f-1})) = abs_{f-1} * inv(rel_f), abs_{-1} = first (NULL = identity);
+ * rel, out float64 [F,16].  One CTA, parallel prefix product. */
+int pwclo_accumulate_poses(const double *rel, int F, const double *first, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

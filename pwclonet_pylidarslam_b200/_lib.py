@@ -48,6 +48,8 @@ SIGNATURES = {
     "pwclo_gather_rows3": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "pwclo_transpose": [_vp, _i, _i, _i, _i, _vp, _vp],
     "pwclo_prepare_scans": [_vp, _vp, _i, _i, _vp, _i, _vp, ctypes.c_ulonglong, _i, _vp, _vp, _vp, _vp],
+    "pwclo_pose_to_matrix": [_vp, _i, _i, _i, _vp, _vp],
+    "pwclo_accumulate_poses": [_vp, _i, _vp, _vp, _vp],
     "pwclo_adam_step": [_vp, _vp, _vp, _vp, ctypes.c_size_t, _i, _f, _f, _f, _f, _f, _f, _vp],
     "pwclo_pose_loss": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
 }

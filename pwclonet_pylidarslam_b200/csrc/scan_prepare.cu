@@ -115,7 +115,7 @@ scan_prepare_kernel(const float4* __restrict__ raw, const long long* __restrict_
   int chunk = ((n + 4 * kPrepCluster - 1) / (4 * kPrepCluster)) * 4;
   const bool too_big = chunk > chunk_cap;            // host sized the keys region from max_points
   if (too_big) chunk = 0;
-  const int lo = min(n, rank * chunk), hi = min(n, lo + chunk);
+  const int lo = rank * chunk, hi = min(n, lo + chunk);       // lo stays a multiple of 4 (may lie beyond n: empty slice)
   const uint2 pkey = make_uint2(seed_lo, seed_hi);
 
   for (int b = tid; b < kPrepBins; b += kPrepThreads) hist[b] = 0;
