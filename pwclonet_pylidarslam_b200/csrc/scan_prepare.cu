@@ -51,7 +51,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 __device__ __forceinline__ unsigned pick4(const uint4& v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
 
 // row-major 3x4 affine map in float64 in the order np.matmul(Tr, [x y z 1]^T) accumulates its 4-term dot
-// products: one multiply, then fused multiply-adds in storage order (oracle/scan_port.affine, checked bit
+// products: one multiply, then fused multiply-adds in storage order (the same expression is checked bit
 // for bit against np.matmul in tests/test_scan_cpu.py)
 __device__ __forceinline__ void affine3x4(const double* __restrict__ T, double x, double y, double z, double& X, double& Y,
                                           double& Z) {
