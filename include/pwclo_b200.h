@@ -224,19 +224,20 @@ int pwclo_adam_step(float *param, const float *grad, float *exp_avg, float *exp_
  * slam/dataset/kitti_odometry_dataset.py:375-397 (Tr transform in float64) and filter_pcd :149-172
  * (drop y > 1.1 and |x|,|z| >= 30, keep `npoints` random survivors without replacement, pad with
  * replacement when there are fewer), plus the optional augmentation transform of :404-446.
- *   raw        packed scans, float32 [total_points,4] (x, y, z, reflectance), 16-byte aligned
- *   offsets    int64 [nscan+1], point offset of every scan in `raw` (device memory)
- *   max_points upper bound of the scan sizes (sizes the shared-memory key store; <= ~190 000)
- *   Tr         float64 [12] (or [nscan,12] when tr_per_scan != 0): rows 0..2 of the 4x4 calibration
- *   post       float64 [nscan,12] applied after the selection, before the float32 cast; NULL = none
- *   seed       the sample is the npoints survivors with the smallest (philox4x32-10 key, index)
- *   out        float32 [nscan,npoints,3];  sel_idx int32 [nscan,npoints] source rows (may be NULL);
- *   survivors  int32 [nscan] points that passed the filter, -1 if a scan exceeded max_points (may be NULL)
- * One launch; every scan point is read from HBM once (16 B per point). */
-int pwclo_prepare_scans(const float *raw, const long long *offsets, int nscan, int max_points,
+ *   raw          packed scans, float32 [total_points,4] (x, y, z, reflectance), 16-byte aligned
+ *   offsets      int64 [nscan+1], point offset of every scan in `raw` (device memory); scans < 2^22 points
+ *   Tr           float64 [12] (or [nscan,12] when tr_per_scan != 0): rows 0..2 of the 4x4 calibration
+ *   post         float64 [nscan,12] applied after the selection, before the float32 cast; NULL = none
+ *   seed         the sample is the npoints survivors with the smallest (philox4x32-10 key, index)
+ *   out          float32 [nscan,npoints,3];  sel_idx int32 [nscan,npoints] source rows (may be NULL);
+ *   survivors    int32 [nscan] points that passed the filter, -1 on an internal capacity overflow (may be NULL)
+ *   workspace    pwclo_prepare_scans_workspace_bytes(total_points, nscan) bytes of device memory, 16-byte aligned
+ * Two launches; every scan point is read from HBM once (16 B per point). */
+size_t pwclo_prepare_scans_workspace_bytes(long long total_points, int nscan);
+int pwclo_prepare_scans(const float *raw, const long long *offsets, int nscan, long long total_points,
                         const double *Tr, int tr_per_scan, const double *post,
                         unsigned long long seed, int npoints, float *out, int32_t *sel_idx,
-                        int32_t *survivors, void *stream);
+                        int32_t *survivors, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- pose post-processing ------------------------------------------------ */
 

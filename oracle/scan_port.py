@@ -34,10 +34,14 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def point_keys(n, scan, seed):
-    """31-bit selection key of every point of scan `scan`"""
-    g = np.arange((n + 3) // 4, dtype=np.uint32)
-    r = philox4x32_10(g, np.uint32(scan), np.uint32(0), np.uint32(0), seed & 0xFFFFFFFF, seed >> 32)
-    return (np.stack(r, axis=1).reshape(-1)[:n] >> np.uint32(1)).astype(np.uint32)
+    """31-bit selection key of every point of scan `scan`: point i uses Philox counter 32*(i//128) + i%32 and
+    output word (i//32)%4 (one call per lane of the warp that streams a 128-point block)"""
+    i = np.arange(n, dtype=np.int64)
+    ctr = (((i >> 7) << 5) | (i & 31)).astype(np.uint32)
+    r = philox4x32_10(ctr, np.uint32(scan), np.uint32(0), np.uint32(0), seed & 0xFFFFFFFF, seed >> 32)
+    word = (i >> 5) & 3
+    k = np.choose(word, r)
+    return (k >> np.uint32(1)).astype(np.uint32)
 
 
 def draws(count, scan, seed):

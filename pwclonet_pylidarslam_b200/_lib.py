@@ -47,7 +47,8 @@ SIGNATURES = {
     "pwclo_tc_selftest": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "pwclo_gather_rows3": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "pwclo_transpose": [_vp, _i, _i, _i, _i, _vp, _vp],
-    "pwclo_prepare_scans": [_vp, _vp, _i, _i, _vp, _i, _vp, ctypes.c_ulonglong, _i, _vp, _vp, _vp, _vp],
+    "pwclo_prepare_scans": [_vp, _vp, _i, ctypes.c_longlong, _vp, _i, _vp, ctypes.c_ulonglong, _i, _vp, _vp, _vp, _vp,
+                            ctypes.c_size_t, _vp],
     "pwclo_pose_to_matrix": [_vp, _i, _i, _i, _vp, _vp],
     "pwclo_accumulate_poses": [_vp, _i, _vp, _vp, _vp],
     "pwclo_adam_step": [_vp, _vp, _vp, _vp, ctypes.c_size_t, _i, _f, _f, _f, _f, _f, _f, _vp],
@@ -73,6 +74,8 @@ def lib():
             fn.restype = ctypes.c_int
         L.pwclo_knn_workspace_bytes.argtypes = [_i, _i, _i]
         L.pwclo_knn_workspace_bytes.restype = ctypes.c_size_t
+        L.pwclo_prepare_scans_workspace_bytes.argtypes = [ctypes.c_longlong, _i]
+        L.pwclo_prepare_scans_workspace_bytes.restype = ctypes.c_size_t
         L.pwclo_version.restype = ctypes.c_char_p
         L.pwclo_error_string.restype = ctypes.c_char_p
         L.pwclo_error_string.argtypes = [ctypes.c_int]

@@ -8,33 +8,38 @@
 // the whole scan.  The result is cast to float32 (optionally after the training augmentation
 // transform, :404-446).
 //
-// Here: ONE kernel, one thread-block cluster of 8 CTAs per scan, every scan point read from HBM exactly
-// once (16 B/point, the roofline of this path).  The random subset is defined by a counter-based
-// generator so that it is reproducible and checkable: point i of scan s gets the 31-bit key
-// philox4x32-10(counter = (i/4, s, 0, 0), key = seed)[i%4] >> 1, and the sample is the npoints survivors
-// with the smallest (key, index), emitted in that order -- a uniformly random subset in uniformly
-// random order, the distribution np.random.choice(replace=False) draws from.
-//   phase 1  each CTA streams its eighth of the scan: float4 loads, fp64 transform, mask, key; keys stay
-//            in shared memory, an 11-bit key histogram is built with shared-memory atomics
-//   phase 2  CTA 0 sums the 8 histograms through distributed shared memory and finds the bin b* in which
-//            the npoints-th smallest key lies
-//   phase 3  every CTA appends its keys below b* to CTA 0's list and those inside b* to a small boundary
-//            list (DSMEM atomics + stores)
-//   phase 4  CTA 0 sorts the boundary list, completes the list to exactly npoints, bitonic-sorts it by
-//            (key, index), gathers the chosen raw points, transforms and writes them
-#include <cooperative_groups.h>
-
+// Here: two launches over the whole batch of scans, every scan point read from HBM once (16 B/point) plus a
+// 2-byte key prefix per point written and read back (L2-resident).  The random subset is defined by a
+// counter-based generator so that it is reproducible and checkable: point i of scan s gets the 31-bit key
+// philox4x32-10(counter = (32*(i/128) + i%32, s, 0, 0), key = seed)[(i/32)%4] >> 1 (one Philox call per lane
+// of the warp that streams a 128-point block), and the sample is the npoints survivors with the smallest
+// (key, index), emitted in that order -- a uniformly random subset in uniformly random order, the
+// distribution np.random.choice(replace=False) draws from.
+//   scan_keys_kernel    grid (8, scans): the 128-point blocks of a scan are dealt round-robin to 8 CTAs; each
+//                       streams its blocks with coalesced float4 loads: fp64 transform, crop, key; it writes the
+//                       15-bit key prefix of every point (or `rejected`) and its 1024-bin histogram of prefixes.
+//                       Pure streaming, no inter-CTA dependency: this is the HBM-bound part.
+//   scan_select_kernel  one CTA per scan, everything in shared memory: sums the 8 histograms and finds the coarse
+//                       bin holding the npoints-th smallest key; streams the prefixes once, re-bins the
+//                       ~npoints + M/1024 candidates below it over their own key range (~npoints/1024 keys per
+//                       bin) and compacts them; counting-sorts them by fine bin with their full keys (recomputed
+//                       densely); the rank of a key inside its bin (~8 comparisons) is its output position;
+//                       gathers the chosen raw points (L2 hits), transforms and writes them.
+// A first version did all of this in one launch with an 8-CTA thread-block cluster per scan (histograms reduced
+// through distributed shared memory): bit-identical results, but its nine cluster barriers and DSMEM latency
+// chains cost ~50 us per cluster with only 33 clusters resident -- 0.26 ms per 128 scans against 0.0x ms here
+// (profiles/r1l_scan_ncu_summary.txt).
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace pwclo {
 
-constexpr int kPrepThreads = 1024;
-constexpr int kPrepCluster = 8;
-constexpr int kPrepBins = 2048;          // top 11 bits of the 31-bit key
-constexpr int kPrepBoundaryCap = 1024;   // keys inside the boundary bin (expected survivors/2048)
-constexpr unsigned kPrepRejected = 0xffffffffu;
+constexpr int kPrepThreads = 512;
+constexpr int kPrepSplit = 8;            // CTAs per scan in the streaming kernel
+constexpr int kPrepBinBits = 10;
+constexpr int kPrepBins = 1 << kPrepBinBits;   // top bits of the 31-bit key
+constexpr int kPrepBoundaryCap = 512;    // keys inside the boundary bin (expected survivors / kPrepBins)
+constexpr int kPrepBlock = 128;          // points per warp step: 4 coalesced float4 loads + one Philox call per lane
+constexpr unsigned short kPrepRejected = 0xffffu;
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
@@ -66,190 +71,260 @@ __device__ __forceinline__ bool keep_point(double X, double Y, double Z) {
 }
 
 struct PrepCtl {
-  int count;       // entries in the main list
-  int bcount;      // entries in the boundary list
-  int bstar;       // boundary bin (kPrepBins when there are fewer survivors than npoints)
-  int below;       // survivors in bins < bstar
-  int survivors;   // M
+  int bstar;       // boundary bin (kPrepBins when there are fewer keys than wanted)
+  int below;       // keys in bins < bstar
+  int bpop;        // keys inside the boundary bin
+  int total;       // all keys of the histogram
+  int ncand;       // compacted candidates
   int pad[3];
 };
 
-// bitonic sort of `len` (power of two) 64-bit keys in shared memory, ascending, all threads of the CTA
-__device__ void bitonic_sort_u64(unsigned long long* a, int len) {
-  for (int k = 2; k <= len; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < (len >> 1); t += blockDim.x) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));     // lower index of the pair
-        const int p = i | j;
-        const bool up = (i & k) == 0;
-        const unsigned long long x = a[i], y = a[p];
-        if ((x > y) == up) { a[i] = y; a[p] = x; }
-      }
-      __syncthreads();
-    }
-  }
+// 31-bit selection key of point i of a scan: lane (i & 31) of the warp that streams the 128-point block
+// i >> 7 draws one Philox counter for its four points i, i+32, i+64, i+96 of that block
+__device__ __forceinline__ unsigned point_key(int i, unsigned scan, uint2 pkey) {
+  const uint4 r = philox4x32_10(make_uint4((unsigned)(((i >> 7) << 5) | (i & 31)), scan, 0u, 0u), pkey);
+  return pick4(r, (i >> 5) & 3) >> 1;
 }
 
-__global__ void __cluster_dims__(kPrepCluster, 1, 1) __launch_bounds__(kPrepThreads, 1)
-scan_prepare_kernel(const float4* __restrict__ raw, const long long* __restrict__ offsets, const double* __restrict__ Tr,
-                    int tr_per_scan, const double* __restrict__ post, unsigned seed_lo, unsigned seed_hi, int npoints,
-                    int chunk_cap, int list_cap, float* __restrict__ out, int* __restrict__ sel_idx,
-                    int* __restrict__ survivors) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned* hist = reinterpret_cast<unsigned*>(smem_raw);                                    // [kPrepBins]
-  unsigned long long* blist = reinterpret_cast<unsigned long long*>(hist + kPrepBins);       // [kPrepBoundaryCap]
-  unsigned long long* list = blist + kPrepBoundaryCap;                                       // [list_cap]
-  unsigned* keys = reinterpret_cast<unsigned*>(list + list_cap);                             // [chunk_cap]
-  __shared__ PrepCtl ctl;
-  __shared__ unsigned warp_tot[kPrepThreads / 32];
-  __shared__ double sT[12], sP[12];
+// exclusive scan of one value per thread over the CTA; returns the exclusive prefix, *total = CTA sum
+__device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* warp_tot, unsigned* total) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned u = __shfl_up_sync(PWCLO_FULL_MASK, incl, o);
+    if (lane >= o) incl += u;
+  }
+  __syncthreads();                                           // previous users of warp_tot are done
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  unsigned before = 0, sum = 0;
+#pragma unroll
+  for (int w = 0; w < kPrepThreads / 32; ++w) {
+    const unsigned c = warp_tot[w];
+    before += w < warp ? c : 0u;
+    sum += c;
+  }
+  *total = sum;
+  return before + incl - v;
+}
 
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
-  const int scan = blockIdx.y;
+// exclusive-scan the 1024-bin histogram (2 bins per thread), write the bin starts and locate the bin in which
+// the `want`-th smallest key lies
+__device__ void scan_locate(const unsigned* hist, unsigned* starts, unsigned* warp_tot, int want_i, PrepCtl* ctl) {
   const int tid = threadIdx.x;
+  const unsigned c0 = hist[2 * tid], c1 = hist[2 * tid + 1];
+  if (tid == 0) ctl->bstar = kPrepBins;
+  unsigned total;
+  const unsigned mine = c0 + c1;
+  const unsigned excl = block_exclusive_scan(mine, warp_tot, &total);      // (its barriers order the bstar reset)
+  starts[2 * tid] = excl;
+  starts[2 * tid + 1] = excl + c0;
+  if (tid == kPrepThreads - 1) { starts[kPrepBins] = total; ctl->total = (int)total; }
+  const unsigned want = (unsigned)want_i;
+  if (excl < want && excl + mine >= want) {                  // exactly one thread when there are >= want keys
+    if (excl + c0 >= want) { ctl->bstar = 2 * tid; ctl->below = (int)excl; ctl->bpop = (int)c0; }
+    else { ctl->bstar = 2 * tid + 1; ctl->below = (int)(excl + c0); ctl->bpop = (int)c1; }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// launch 1: stream every scan point once
+__global__ void __launch_bounds__(kPrepThreads, 2)
+scan_keys_kernel(const float4* __restrict__ raw, const long long* __restrict__ offsets, const double* __restrict__ Tr,
+                 int tr_per_scan, unsigned seed_lo, unsigned seed_hi, unsigned short* __restrict__ pref,
+                 unsigned* __restrict__ ghist) {
+  __shared__ unsigned hist[kPrepBins];
+  __shared__ double sT[12];
+  const int rank = blockIdx.x, scan = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kPrepThreads / 32;
   const long long base = offsets[scan];
   const int n = (int)(offsets[scan + 1] - base);
   const float4* pts = raw + base;
-  // eighths rounded up to whole groups of 4 points (one Philox call serves 4 points)
-  int chunk = ((n + 4 * kPrepCluster - 1) / (4 * kPrepCluster)) * 4;
-  const bool too_big = chunk > chunk_cap;            // host sized the keys region from max_points
-  if (too_big) chunk = 0;
-  const int lo = rank * chunk, hi = min(n, lo + chunk);       // lo stays a multiple of 4 (may lie beyond n: empty slice)
+  unsigned short* pf = pref + base;
+  const int nblk = (n + kPrepBlock - 1) / kPrepBlock;
   const uint2 pkey = make_uint2(seed_lo, seed_hi);
-
   for (int b = tid; b < kPrepBins; b += kPrepThreads) hist[b] = 0;
+  if (tid < 12) sT[tid] = Tr[(tr_per_scan ? (size_t)scan * 12 : 0) + tid];
+  __syncthreads();
+  // a warp takes 128 consecutive points per step: 4 x 512 B coalesced loads, one Philox call per lane.  Blocks are
+  // dealt round-robin (a scan is stored beam by beam and whole beams are cropped away: contiguous eighths would
+  // leave some CTAs with all the survivors -- and all the histogram atomics)
+  for (int g = rank + warp * kPrepSplit; g < nblk; g += kWarps * kPrepSplit) {
+    const int b0 = g << 7;
+    float4 p[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = b0 + 32 * k + lane;
+      if (i < n) p[k] = __ldcs(pts + i);
+    }
+    const uint4 r = philox4x32_10(make_uint4((unsigned)((g << 5) | lane), (unsigned)scan, 0u, 0u), pkey);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = b0 + 32 * k + lane;
+      if (i < n) {
+        unsigned short v = kPrepRejected;
+        double X, Y, Z;
+        affine3x4(sT, (double)p[k].x, (double)p[k].y, (double)p[k].z, X, Y, Z);
+        if (keep_point(X, Y, Z)) {
+          const unsigned top15 = pick4(r, k) >> 17;              // (key31 = word >> 1) >> 16
+          v = (unsigned short)top15;
+          atomicAdd(&hist[top15 >> (15 - kPrepBinBits)], 1u);
+        }
+        pf[i] = v;
+      }
+    }
+  }
+  __syncthreads();
+  unsigned* gh = ghist + ((size_t)scan * kPrepSplit + rank) * kPrepBins;
+  for (int b = tid; b < kPrepBins; b += kPrepThreads) gh[b] = hist[b];
+}
+
+// list entry: key31 << 32 | fine bin << 22 | point index (< 2^22); the bin is a monotonic function of the key,
+// so comparing whole entries orders by (key, index)
+constexpr int kPrepIdxBits = 22;
+constexpr unsigned kPrepIdxMask = (1u << kPrepIdxBits) - 1u;
+constexpr int kPrepCandSlack = 2048;     // candidates beyond npoints (expected M/1024)
+
+// ---------------------------------------------------------------------------------------------------------------
+// launch 2: one CTA per scan selects, orders, gathers
+__global__ void __launch_bounds__(kPrepThreads, 1)
+scan_select_kernel(const float4* __restrict__ raw, const long long* __restrict__ offsets, const double* __restrict__ Tr,
+                   int tr_per_scan, const double* __restrict__ post, unsigned seed_lo, unsigned seed_hi, int npoints,
+                   const unsigned short* __restrict__ pref, const unsigned* __restrict__ ghist, float* __restrict__ out,
+                   int* __restrict__ sel_idx, int* __restrict__ survivors) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned* hist = reinterpret_cast<unsigned*>(smem_raw);                    // [kPrepBins]
+  unsigned* starts = hist + kPrepBins;                                       // [kPrepBins + 2]
+  unsigned long long* list = reinterpret_cast<unsigned long long*>(starts + kPrepBins + 2);   // [npoints + kPrepBoundaryCap]
+  unsigned* cand = reinterpret_cast<unsigned*>(list + npoints + kPrepBoundaryCap);            // [npoints + kPrepCandSlack]
+  __shared__ PrepCtl ctl;
+  __shared__ unsigned warp_tot[kPrepThreads / 32];
+  __shared__ double sT[12], sP[12];
+  const int list_cap = npoints + kPrepBoundaryCap, cand_cap = npoints + kPrepCandSlack;
+  const int scan = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const long long base = offsets[scan];
+  const int n = (int)(offsets[scan + 1] - base);
+  const float4* pts = raw + base;
+  const unsigned short* pf = pref + base;
+  const uint2 pkey = make_uint2(seed_lo, seed_hi);
+  const bool too_big = n > (int)kPrepIdxMask;
+
+  {  // coarse histogram of the scan = sum of the streaming CTAs' histograms
+    const unsigned* gh = ghist + (size_t)scan * kPrepSplit * kPrepBins;
+    for (int b = tid; b < kPrepBins; b += kPrepThreads) {
+      unsigned c = 0;
+#pragma unroll
+      for (int r = 0; r < kPrepSplit; ++r) c += gh[r * kPrepBins + b];
+      hist[b] = c;
+    }
+  }
   if (tid < 12) {
     sT[tid] = Tr[(tr_per_scan ? (size_t)scan * 12 : 0) + tid];
     sP[tid] = post ? post[(size_t)scan * 12 + tid] : 0.0;
   }
-  if (tid == 0) { ctl.count = 0; ctl.bcount = 0; ctl.bstar = kPrepBins; ctl.below = 0; ctl.survivors = 0; }
+  if (tid == 0) ctl.ncand = 0;
   __syncthreads();
+  scan_locate(hist, starts, warp_tot, npoints, &ctl);
+  const int cstar = ctl.bstar;
+  const int M = ctl.total;
+  const bool short_mode = cstar == kPrepBins || too_big;   // fewer survivors than npoints: keep them all, in index order
+  __syncthreads();
+  int have;
 
-  // ---- phase 1: stream the slice once
-  for (int g = (lo >> 2) + tid; (g << 2) < hi; g += kPrepThreads) {
-    const uint4 r = philox4x32_10(make_uint4((unsigned)g, (unsigned)scan, 0u, 0u), pkey);
-    const int i0 = g << 2;
-    float4 p[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (i0 + j < hi) p[j] = __ldcs(pts + i0 + j);          // streaming: read once
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (i0 + j < hi) {
-        double X, Y, Z;
-        affine3x4(sT, (double)p[j].x, (double)p[j].y, (double)p[j].z, X, Y, Z);
-        const unsigned k31 = pick4(r, j) >> 1;
-        const bool keep = keep_point(X, Y, Z);
-        keys[i0 + j - lo] = keep ? k31 : kPrepRejected;
-        if (keep) atomicAdd(&hist[k31 >> 20], 1u);
-      }
-    }
-  }
-  cluster.sync();
-
-  // ---- phase 2: CTA 0 reduces the histograms over the cluster and locates the boundary bin
-  if (rank == 0) {
-    unsigned c0 = 0, c1 = 0;
-    for (int r = 0; r < kPrepCluster; ++r) {
-      const unsigned* h = cluster.map_shared_rank(hist, r);
-      c0 += h[2 * tid];
-      c1 += h[2 * tid + 1];
-    }
-    // exclusive scan of (c0 + c1) over the 1024 threads
-    const unsigned mine = c0 + c1;
-    unsigned incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned v = __shfl_up_sync(PWCLO_FULL_MASK, incl, o);
-      if ((tid & 31) >= o) incl += v;
-    }
-    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
-    __syncthreads();
-    if (tid < 32) {
-      unsigned w = warp_tot[tid], wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned v = __shfl_up_sync(PWCLO_FULL_MASK, wi, o);
-        if (tid >= o) wi += v;
-      }
-      warp_tot[tid] = wi - w;                                  // exclusive warp offsets
-      if (tid == 31) ctl.survivors = (int)wi;
-    }
-    __syncthreads();
-    const unsigned excl = warp_tot[tid >> 5] + incl - mine;
-    const unsigned want = (unsigned)npoints;
-    if (excl < want && excl + mine >= want) {                  // exactly one thread when M >= npoints
-      if (excl + c0 >= want) { ctl.bstar = 2 * tid; ctl.below = (int)excl; }
-      else { ctl.bstar = 2 * tid + 1; ctl.below = (int)(excl + c0); }
-    }
-    __syncthreads();
-  }
-  cluster.sync();
-  PrepCtl* ctl0 = cluster.map_shared_rank(&ctl, 0);
-  const int bstar = ctl0->bstar;
-  const bool short_mode = bstar == kPrepBins;                  // fewer survivors than npoints: keep them all, by index
-
-  // ---- phase 3: append the selected keys to CTA 0's lists
-  {
-    unsigned long long* list0 = cluster.map_shared_rank(list, 0);
-    unsigned long long* blist0 = cluster.map_shared_rank(blist, 0);
-    for (int j = tid; j < hi - lo; j += kPrepThreads) {
-      const unsigned k = keys[j];
-      if (k == kPrepRejected) continue;
-      const int bin = (int)(k >> 20);
-      const unsigned idx = (unsigned)(lo + j);
-      if (short_mode) {
-        const int pos = atomicAdd(&ctl0->count, 1);
-        if (pos < list_cap) list0[pos] = (unsigned long long)idx;
-      } else if (bin < bstar) {
-        const int pos = atomicAdd(&ctl0->count, 1);
-        if (pos < list_cap) list0[pos] = ((unsigned long long)k << 32) | idx;
-      } else if (bin == bstar) {
-        const int pos = atomicAdd(&ctl0->bcount, 1);
-        if (pos < kPrepBoundaryCap) blist0[pos] = ((unsigned long long)k << 32) | idx;
-      }
-    }
-  }
-  cluster.sync();
-  if (rank != 0) return;          // nothing reads this CTA's shared memory any more
-
-  // ---- phase 4 (CTA 0): complete, sort, gather
-  const int M = ctl.survivors;
-  int have = min(ctl.count, list_cap);
-  bool overflow = too_big || ctl.count > list_cap;
   if (!short_mode) {
-    const int bc = ctl.bcount;
-    if (bc > kPrepBoundaryCap) overflow = true;
-    const int bn = min(bc, kPrepBoundaryCap);
-    for (int j = bn + tid; j < kPrepBoundaryCap; j += kPrepThreads) blist[j] = ~0ull;
+    // Only keys whose 15-bit prefix is below R = (cstar+1) << 5 can be chosen: about npoints + M/1024 candidates.
+    // Re-bin exactly those over [0, R) so that a bin holds ~npoints/1024 keys whatever the survivor count is, and
+    // compact them (one shared-memory atomic per warp step).
+    const unsigned R = (unsigned)(cstar + 1) << (15 - kPrepBinBits);
+    for (int b = tid; b < kPrepBins; b += kPrepThreads) hist[b] = 0;
     __syncthreads();
-    bitonic_sort_u64(blist, kPrepBoundaryCap);
-    const int need = min(npoints - have, bn);
-    for (int j = tid; j < need; j += kPrepThreads) list[have + j] = blist[j];
-    have += max(need, 0);
+    for (int i0 = 0; i0 < n; i0 += kPrepThreads) {
+      const int i = i0 + tid;
+      const unsigned t15 = i < n ? (unsigned)pf[i] : (unsigned)kPrepRejected;
+      const bool is_c = t15 < R;
+      const unsigned m = __ballot_sync(PWCLO_FULL_MASK, is_c);
+      if (m) {
+        unsigned wbase = 0;
+        if (lane == 0) wbase = (unsigned)atomicAdd(&ctl.ncand, __popc(m));
+        wbase = __shfl_sync(PWCLO_FULL_MASK, wbase, 0);
+        if (is_c) {
+          const unsigned fb = (t15 << kPrepBinBits) / R;
+          atomicAdd(&hist[fb], 1u);
+          const unsigned slot = wbase + __popc(m & ((1u << lane) - 1u));
+          if (slot < (unsigned)cand_cap) cand[slot] = (fb << kPrepIdxBits) | (unsigned)i;
+        }
+      }
+    }
+    __syncthreads();
+    scan_locate(hist, starts, warp_tot, npoints, &ctl);
+    const int bstar = ctl.bstar, below = ctl.below, bpop = ctl.bpop;
+    const int ncand = min(ctl.ncand, cand_cap);
+    const bool overflow = ctl.ncand > cand_cap || bpop > kPrepBoundaryCap;
+    // counting sort by fine bin, with the full keys (dense: every thread has work)
+    for (int c = tid; c < ncand; c += kPrepThreads) {
+      const unsigned e = cand[c];
+      const unsigned bin = e >> kPrepIdxBits;
+      if (bin > (unsigned)bstar) continue;
+      const unsigned slot = starts[bin] + (atomicSub(&hist[bin], 1u) - 1u);
+      if (slot < (unsigned)list_cap)
+        list[slot] = ((unsigned long long)point_key((int)(e & kPrepIdxMask), (unsigned)scan, pkey) << 32) | e;
+    }
+    __syncthreads();
+    const int filled = min(list_cap, below + bpop);
+    if (tid == 0 && survivors) survivors[scan] = overflow ? -1 : M;
+    // rank inside the bin = final position; gather, transform, write
+    for (int j = tid; j < filled; j += kPrepThreads) {
+      const unsigned long long e = list[j];
+      const unsigned bin = ((unsigned)e >> kPrepIdxBits) & (kPrepBins - 1);
+      const int s0 = (int)starts[bin], e0 = min((int)starts[bin + 1], filled);
+      int pos = s0;
+      for (int i = s0; i < e0; ++i) pos += list[i] < e ? 1 : 0;
+      if (pos >= npoints) continue;                                 // the boundary bin holds a few keys too many
+      const int idx = (int)((unsigned)e & kPrepIdxMask);
+      const float4 p = __ldg(pts + idx);
+      double X, Y, Z;
+      affine3x4(sT, (double)p.x, (double)p.y, (double)p.z, X, Y, Z);
+      if (post) { double A, B, C; affine3x4(sP, X, Y, Z, A, B, C); X = A; Y = B; Z = C; }
+      float* o = out + ((size_t)scan * npoints + pos) * 3;
+      o[0] = (float)X; o[1] = (float)Y; o[2] = (float)Z;
+      if (sel_idx) sel_idx[(size_t)scan * npoints + pos] = idx;
+    }
+    return;
   }
-  int p2 = 1;
-  while (p2 < max(have, 2)) p2 <<= 1;
-  for (int j = have + tid; j < p2; j += kPrepThreads) list[j] = ~0ull;
-  __syncthreads();
-  bitonic_sort_u64(list, p2);
 
-  if (tid == 0 && survivors) survivors[scan] = overflow ? -1 : M;
+  // ---- fewer survivors than npoints (rare): all of them in ascending index, then draws with replacement
+  {
+    unsigned running = 0;
+    for (int i0 = 0; i0 < n && !too_big; i0 += kPrepThreads) {
+      const int i = i0 + tid;
+      const bool keep = i < n && pf[i] != kPrepRejected;
+      unsigned total;
+      const unsigned excl = block_exclusive_scan(keep ? 1u : 0u, warp_tot, &total);
+      if (keep && running + excl < (unsigned)list_cap) list[running + excl] = (unsigned long long)(unsigned)i;
+      running += total;
+    }
+    __syncthreads();
+    have = too_big ? 0 : min(M, list_cap);
+    if (tid == 0 && survivors) survivors[scan] = too_big ? -1 : M;
+  }
   for (int j = tid; j < npoints; j += kPrepThreads) {
     int idx;
     if (j < have) {
-      idx = (int)(unsigned)(list[j] & 0xffffffffull);
+      idx = (int)(unsigned)list[j];
     } else {
-      // pad with draws with replacement (from the survivors, or from the whole scan when there are none)
+      // draws with replacement (from the survivors, or from the whole scan when there are none)
       const int d = j - have;
       const uint4 r = philox4x32_10(make_uint4((unsigned)(d >> 2), (unsigned)scan, 1u, 0u), pkey);
       const unsigned u = pick4(r, d & 3);
-      idx = have > 0 ? (int)(unsigned)(list[__umulhi(u, (unsigned)have)] & 0xffffffffull) : (n > 0 ? (int)__umulhi(u, (unsigned)n) : -1);
+      idx = have > 0 ? (int)(unsigned)list[__umulhi(u, (unsigned)have)] : (n > 0 ? (int)__umulhi(u, (unsigned)n) : -1);
     }
     float ox = 0.f, oy = 0.f, oz = 0.f;
     if (idx >= 0) {
-      const float4 p = pts[idx];
+      const float4 p = __ldg(pts + idx);
       double X, Y, Z;
       affine3x4(sT, (double)p.x, (double)p.y, (double)p.z, X, Y, Z);
       if (post) { double A, B, C; affine3x4(sP, X, Y, Z, A, B, C); X = A; Y = B; Z = C; }
@@ -263,27 +338,41 @@ scan_prepare_kernel(const float4* __restrict__ raw, const long long* __restrict_
 
 }  // namespace pwclo
 
-PWCLO_API int pwclo_prepare_scans(const float* raw, const long long* offsets, int nscan, int max_points, const double* Tr,
-                                  int tr_per_scan, const double* post, unsigned long long seed, int npoints, float* out,
-                                  int32_t* sel_idx, int32_t* survivors, void* stream) {
+// workspace: key prefixes (2 B per point, rounded to 256 B) + 8 x 1024 histogram counters per scan
+PWCLO_API size_t pwclo_prepare_scans_workspace_bytes(long long total_points, int nscan) {
+  if (total_points < 0 || nscan < 0) return 0;
+  const size_t pref = (((size_t)total_points * 2 + 255) / 256) * 256;
+  return pref + (size_t)nscan * pwclo::kPrepSplit * pwclo::kPrepBins * 4;
+}
+
+PWCLO_API int pwclo_prepare_scans(const float* raw, const long long* offsets, int nscan, long long total_points,
+                                  const double* Tr, int tr_per_scan, const double* post, unsigned long long seed, int npoints,
+                                  float* out, int32_t* sel_idx, int32_t* survivors, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
   using namespace pwclo;
-  if (!raw || !offsets || !Tr || !out || nscan < 0 || npoints <= 0 || max_points <= 0) return PWCLO_EINVAL;
-  if (((uintptr_t)raw & 15) != 0) return PWCLO_EINVAL;
+  if (!raw || !offsets || !Tr || !out || !workspace || nscan < 0 || npoints <= 0 || total_points < 0) return PWCLO_EINVAL;
+  if (((uintptr_t)raw & 15) != 0 || ((uintptr_t)workspace & 15) != 0) return PWCLO_EINVAL;
+  if (workspace_bytes < pwclo_prepare_scans_workspace_bytes(total_points, nscan)) return PWCLO_EINVAL;
   if (nscan == 0) return PWCLO_OK;
-  int chunk_cap = ((max_points + 4 * kPrepCluster - 1) / (4 * kPrepCluster)) * 4;
-  int list_cap = 2;
-  while (list_cap < npoints) list_cap <<= 1;
-  const size_t smem = (size_t)kPrepBins * 4 + (size_t)kPrepBoundaryCap * 8 + (size_t)list_cap * 8 + (size_t)chunk_cap * 4;
-  if (smem > 227 * 1024 - 1024) return PWCLO_EUNSUPPORTED;
+  const size_t smem = (size_t)(kPrepBins * 2 + 2) * 4 + (size_t)(npoints + kPrepBoundaryCap) * 8 +
+                      (size_t)(npoints + kPrepCandSlack) * 4;
+  if (smem > 226 * 1024) return PWCLO_EUNSUPPORTED;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(scan_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(scan_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  dim3 grid(kPrepCluster, nscan, 1);
-  scan_prepare_kernel<<<grid, kPrepThreads, smem, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(raw), offsets, Tr, tr_per_scan ? 1 : 0, post, (unsigned)(seed & 0xffffffffull),
-      (unsigned)(seed >> 32), npoints, chunk_cap, list_cap, out, sel_idx, survivors);
+  unsigned short* pref = reinterpret_cast<unsigned short*>(workspace);
+  unsigned* ghist = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(workspace) +
+                                                (((size_t)total_points * 2 + 255) / 256) * 256);
+  const unsigned slo = (unsigned)(seed & 0xffffffffull), shi = (unsigned)(seed >> 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  scan_keys_kernel<<<dim3(kPrepSplit, nscan, 1), kPrepThreads, 0, st>>>(reinterpret_cast<const float4*>(raw), offsets, Tr,
+                                                                       tr_per_scan ? 1 : 0, slo, shi, pref, ghist);
+  int rc = launch_status();
+  if (rc) return rc;
+  scan_select_kernel<<<nscan, kPrepThreads, smem, st>>>(reinterpret_cast<const float4*>(raw), offsets, Tr, tr_per_scan ? 1 : 0,
+                                                        post, slo, shi, npoints, pref, ghist, out, sel_idx, survivors);
   return launch_status();
 }

@@ -2,7 +2,7 @@
 
 Replaces, per frame, the host numpy code of slam/dataset/kitti_odometry_dataset.py:375-397 (`Tr`
 transform in float64) and `filter_pcd` :149-172 (ground / range crop + `npoints` random survivors), and
-the optional augmentation transform :404-446, by ONE launch of `pwclo_prepare_scans` over a packed batch
+the optional augmentation transform :404-446, by `pwclo_prepare_scans` (two launches) over a packed batch
 of scans.  There is no CPU path: tensors must live on the GPU.
 """
 import ctypes
@@ -39,7 +39,8 @@ def pack_pairs(scans1, scans2, pin=True):
 
 
 def prepare_scans(raw, offsets, Tr, npoints, seed, post=None, max_points=None, return_index=False):
-    """raw float32 [total,4] CUDA, offsets int64 [S+1] CUDA, Tr float64 [3,4] (or [S,3,4]) CUDA ->
+    """(`max_points` is accepted for compatibility and ignored.)
+    raw float32 [total,4] CUDA, offsets int64 [S+1] CUDA, Tr float64 [3,4] (or [S,3,4]) CUDA ->
     clouds float32 [S,npoints,3] (+ int32 [S,npoints] source rows, int32 [S] survivors)."""
     for t, name, dt in ((raw, "raw", torch.float32), (offsets, "offsets", torch.int64), (Tr, "Tr", torch.float64)):
         if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dt and t.is_contiguous()):
@@ -50,14 +51,15 @@ def prepare_scans(raw, offsets, Tr, npoints, seed, post=None, max_points=None, r
         raise RuntimeError("Tr must be [3,4] or [S,3,4]")
     if post is not None and not (post.is_cuda and post.dtype == torch.float64 and post.is_contiguous() and post.numel() == 12 * S):
         raise RuntimeError("post must be a contiguous float64 CUDA tensor [S,3,4]")
-    if max_points is None:
-        max_points = int((offsets[1:] - offsets[:-1]).max()) if S else 1      # one small D2H read; pass it to avoid
+    total = int(raw.shape[0])
+    L = _lib.lib()
+    ws = torch.empty(max(16, L.pwclo_prepare_scans_workspace_bytes(total, S)), dtype=torch.uint8, device=raw.device)
     out = torch.empty((S, npoints, 3), dtype=torch.float32, device=raw.device)
     idx = torch.empty((S, npoints), dtype=torch.int32, device=raw.device)
     surv = torch.empty((S,), dtype=torch.int32, device=raw.device)
     p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
     with torch.cuda.device(raw.device):
-        _lib.check(_lib.lib().pwclo_prepare_scans(p(raw), p(offsets), S, int(max_points), p(Tr), 1 if per_scan else 0, p(post),
-                                                  ctypes.c_ulonglong(int(seed) & (2 ** 64 - 1)), int(npoints), p(out), p(idx),
-                                                  p(surv), _lib.stream_ptr()), "prepare_scans")
+        _lib.check(L.pwclo_prepare_scans(p(raw), p(offsets), S, total, p(Tr), 1 if per_scan else 0, p(post),
+                                         ctypes.c_ulonglong(int(seed) & (2 ** 64 - 1)), int(npoints), p(out), p(idx), p(surv),
+                                         p(ws), ws.numel(), _lib.stream_ptr()), "prepare_scans")
     return (out, idx, surv) if return_index else out
