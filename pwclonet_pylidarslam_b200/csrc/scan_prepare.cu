@@ -242,20 +242,54 @@ scan_select_kernel(const float4* __restrict__ raw, const long long* __restrict__
     const unsigned R = (unsigned)(cstar + 1) << (15 - kPrepBinBits);
     for (int b = tid; b < kPrepBins; b += kPrepThreads) hist[b] = 0;
     __syncthreads();
-    for (int i0 = 0; i0 < n; i0 += kPrepThreads) {
-      const int i = i0 + tid;
-      const unsigned t15 = i < n ? (unsigned)pf[i] : (unsigned)kPrepRejected;
-      const bool is_c = t15 < R;
-      const unsigned m = __ballot_sync(PWCLO_FULL_MASK, is_c);
-      if (m) {
-        unsigned wbase = 0;
-        if (lane == 0) wbase = (unsigned)atomicAdd(&ctl.ncand, __popc(m));
-        wbase = __shfl_sync(PWCLO_FULL_MASK, wbase, 0);
-        if (is_c) {
-          const unsigned fb = (t15 << kPrepBinBits) / R;
-          atomicAdd(&hist[fb], 1u);
-          const unsigned slot = wbase + __popc(m & ((1u << lane) - 1u));
-          if (slot < (unsigned)cand_cap) cand[slot] = (fb << kPrepIdxBits) | (unsigned)i;
+    // 8 prefixes per 16-byte load (aligned on the whole buffer: the first / last load of a scan may straddle its
+    // neighbours and is masked), 4 loads in flight per thread
+    const long long a0 = base & ~7ll;
+    const uint4* pv = reinterpret_cast<const uint4*>(pref + a0);
+    const int nvec = (int)((base + n - a0 + 7) >> 3);
+    const int shift = (int)(base - a0);
+    for (int v0 = 0; v0 < nvec; v0 += 4 * kPrepThreads) {
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u * kPrepThreads + tid;
+        q[u] = v < nvec ? __ldg(pv + v) : make_uint4(~0u, ~0u, ~0u, ~0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i_first = ((v0 + u * kPrepThreads + tid) << 3) - shift;          // scan index of the first of 8
+        const unsigned w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+        unsigned cmask = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const unsigned t15 = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+          const int i = i_first + e;
+          if (t15 < R && i >= 0 && i < n) cmask |= 1u << e;
+        }
+        const unsigned c = __popc(cmask);
+        // exclusive prefix of c over the warp, one shared-memory atomic per warp
+        unsigned incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned t = __shfl_up_sync(PWCLO_FULL_MASK, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const unsigned wtotal = __shfl_sync(PWCLO_FULL_MASK, incl, 31);
+        if (wtotal) {
+          unsigned wbase = 0;
+          if (lane == 0) wbase = (unsigned)atomicAdd(&ctl.ncand, (int)wtotal);
+          wbase = __shfl_sync(PWCLO_FULL_MASK, wbase, 0);
+          unsigned slot = wbase + incl - c;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (cmask & (1u << e)) {
+              const unsigned t15 = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+              const unsigned fb = (t15 << kPrepBinBits) / R;
+              atomicAdd(&hist[fb], 1u);
+              if (slot < (unsigned)cand_cap) cand[slot] = (fb << kPrepIdxBits) | (unsigned)(i_first + e);
+              ++slot;
+            }
+          }
         }
       }
     }
@@ -276,22 +310,38 @@ scan_select_kernel(const float4* __restrict__ raw, const long long* __restrict__
     __syncthreads();
     const int filled = min(list_cap, below + bpop);
     if (tid == 0 && survivors) survivors[scan] = overflow ? -1 : M;
-    // rank inside the bin = final position; gather, transform, write
-    for (int j = tid; j < filled; j += kPrepThreads) {
-      const unsigned long long e = list[j];
-      const unsigned bin = ((unsigned)e >> kPrepIdxBits) & (kPrepBins - 1);
-      const int s0 = (int)starts[bin], e0 = min((int)starts[bin + 1], filled);
-      int pos = s0;
-      for (int i = s0; i < e0; ++i) pos += list[i] < e ? 1 : 0;
-      if (pos >= npoints) continue;                                 // the boundary bin holds a few keys too many
-      const int idx = (int)((unsigned)e & kPrepIdxMask);
-      const float4 p = __ldg(pts + idx);
-      double X, Y, Z;
-      affine3x4(sT, (double)p.x, (double)p.y, (double)p.z, X, Y, Z);
-      if (post) { double A, B, C; affine3x4(sP, X, Y, Z, A, B, C); X = A; Y = B; Z = C; }
-      float* o = out + ((size_t)scan * npoints + pos) * 3;
-      o[0] = (float)X; o[1] = (float)Y; o[2] = (float)Z;
-      if (sel_idx) sel_idx[(size_t)scan * npoints + pos] = idx;
+    // rank inside the bin = final position; gather, transform, write -- 4 entries per thread step so that the four
+    // gathers are in flight together
+    for (int j0 = 0; j0 < filled; j0 += 4 * kPrepThreads) {
+      int pos[4], idx[4];
+      float4 p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * kPrepThreads + tid;
+        pos[u] = -1;
+        idx[u] = 0;
+        if (j < filled) {
+          const unsigned long long e = list[j];
+          const unsigned bin = ((unsigned)e >> kPrepIdxBits) & (kPrepBins - 1);
+          const int s0 = (int)starts[bin], e0 = min((int)starts[bin + 1], filled);
+          int ps = s0;
+          for (int i = s0; i < e0; ++i) ps += list[i] < e ? 1 : 0;
+          if (ps < npoints) { pos[u] = ps; idx[u] = (int)((unsigned)e & kPrepIdxMask); }   // the boundary bin holds a few too many
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (pos[u] >= 0) p[u] = __ldg(pts + idx[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (pos[u] < 0) continue;
+        double X, Y, Z;
+        affine3x4(sT, (double)p[u].x, (double)p[u].y, (double)p[u].z, X, Y, Z);
+        if (post) { double A, B, C; affine3x4(sP, X, Y, Z, A, B, C); X = A; Y = B; Z = C; }
+        float* o = out + ((size_t)scan * npoints + pos[u]) * 3;
+        o[0] = (float)X; o[1] = (float)Y; o[2] = (float)Z;
+        if (sel_idx) sel_idx[(size_t)scan * npoints + pos[u]] = idx[u];
+      }
     }
     return;
   }
