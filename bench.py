@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="train = BASELINE config 5: forward+backward+all-reduce+Adam, 8 pairs per GPU x 16384 points")
+    ap.add_argument("--no-graph", action="store_true", help="train mode: eager step instead of the captured CUDA graph")
     ap.add_argument("--train-points", type=int, default=16384)
     ap.add_argument("--train-pairs-per-gpu", type=int, default=8)
     return ap.parse_args()
@@ -221,11 +222,24 @@ def run_train(args, world, rank, local):
             dist.barrier()
         torch.cuda.synchronize()
 
+    graphed = not args.no_graph
+    graph_note = "whole step (zero_grad, forward, loss, backward, all-reduce, Adam) replayed as one CUDA graph"
+    if graphed:
+        try:
+            tr.capture(res)
+        except Exception as e:                      # report the eager number rather than nothing, and say why
+            graphed, graph_note = False, f"CUDA-graph capture failed ({type(e).__name__}: {e}); eager step"
+            tr.drop_graph()
+            torch.cuda.synchronize()
+    else:
+        graph_note = "eager step (one launch per op, host-bound)"
+    step_fn = tr.train_step_graphed if graphed else tr.train_step
+
     def step_resident():
-        return tr.train_step(res)[0]
+        return step_fn(res)[0]
 
     def step_e2e():
-        return tr.train_step([b.to(dev, non_blocking=True) for b in pin])[0].cpu()
+        return step_fn(pin if graphed else [b.to(dev, non_blocking=True) for b in pin])[0].cpu()
 
     def timed(fn, steps):
         evs = []
@@ -280,6 +294,7 @@ def run_train(args, world, rank, local):
                                        "train-mode BatchNorm + dropout, one all-reduce of the flat gradient arena, Adam",
                            "pairs_per_gpu": P, "points": N_POINTS, "l2": "flushed between timed steps (256 MB write)",
                            "parallelism": f"data parallel x{world}, one NCCL all-reduce of {tr.arena.numel} fp32 per step",
+                           "execution": graph_note,
                            "note": "sampling / neighbour / grouping ops and the loss on the sm_100a kernels; 1x1 convs, BN and "
                                    "their backward by torch (fused-layer backward is not built)"},
                 "e2e": {"value": world * P * args.steps / (ms_e2e * 1e-3), "unit": UNIT,

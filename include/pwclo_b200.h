@@ -217,6 +217,12 @@ int pwclo_pose_loss(const float *pred, const float *gt, const float *s, int B, i
 int pwclo_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, size_t n,
                     int step, float lr, float beta1, float beta2, float eps, float weight_decay,
                     float grad_scale, void *stream);
+/* The same update with the step counter and the learning rate in device memory, so that a training step can
+ * be captured once in a CUDA graph and replayed: state_i[0] = completed steps (incremented by the call),
+ * state_f[0] = learning rate (the host may rewrite it between replays), state_f[1..2] = scratch. */
+int pwclo_adam_step_dev(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, size_t n,
+                        int32_t *state_i, float *state_f, float beta1, float beta2, float eps,
+                        float weight_decay, float grad_scale, void *stream);
 
 /* ---- input pipeline ----------------------------------------------------------- */
 

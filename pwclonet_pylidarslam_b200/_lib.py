@@ -52,6 +52,7 @@ SIGNATURES = {
     "pwclo_pose_to_matrix": [_vp, _i, _i, _i, _vp, _vp],
     "pwclo_accumulate_poses": [_vp, _i, _vp, _vp, _vp],
     "pwclo_adam_step": [_vp, _vp, _vp, _vp, ctypes.c_size_t, _i, _f, _f, _f, _f, _f, _f, _vp],
+    "pwclo_adam_step_dev": [_vp, _vp, _vp, _vp, ctypes.c_size_t, _vp, _vp, _f, _f, _f, _f, _f, _vp],
     "pwclo_pose_loss": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
 }
 

@@ -149,7 +149,59 @@ adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
     adam_one(p[i], g[i], m[i], v[i], lr_over_bc1, b1, b2, eps, wd, sqrt_bc2, gscale);
 }
 
+// Device-resident step counter and learning rate, so that a whole training step (forward, backward,
+// all-reduce, Adam) can be captured once in a CUDA graph and replayed: nothing step-dependent is baked into
+// kernel arguments.  state_i[0] = step count (incremented here), state_f = {lr (written by the host between
+// replays), lr / (1 - beta1^t), sqrt(1 - beta2^t)} computed in double exactly as the host path does.
+__global__ void adam_tick_kernel(int* __restrict__ state_i, float* __restrict__ state_f, float beta1, float beta2) {
+  const int t = state_i[0] + 1;
+  state_i[0] = t;
+  const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
+  state_f[1] = (float)((double)state_f[0] / bc1);
+  state_f[2] = (float)sqrt(bc2);
+}
+
+__global__ void __launch_bounds__(256)
+adam_step_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                     size_t n, const float* __restrict__ state_f, float b1, float b2, float eps, float wd, float gscale) {
+  const float lr_over_bc1 = state_f[1], sqrt_bc2 = state_f[2];
+  const size_t n4 = n >> 2;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adam_one(pp.x, gg.x, mm.x, vv.x, lr_over_bc1, b1, b2, eps, wd, sqrt_bc2, gscale);
+    adam_one(pp.y, gg.y, mm.y, vv.y, lr_over_bc1, b1, b2, eps, wd, sqrt_bc2, gscale);
+    adam_one(pp.z, gg.z, mm.z, vv.z, lr_over_bc1, b1, b2, eps, wd, sqrt_bc2, gscale);
+    adam_one(pp.w, gg.w, mm.w, vv.w, lr_over_bc1, b1, b2, eps, wd, sqrt_bc2, gscale);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    adam_one(p[i], g[i], m[i], v[i], lr_over_bc1, b1, b2, eps, wd, sqrt_bc2, gscale);
+}
+
 }  // namespace pwclo
+
+PWCLO_API int pwclo_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
+                                  int32_t* state_i, float* state_f, float beta1, float beta2, float eps, float weight_decay,
+                                  float grad_scale, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !state_i || !state_f) return PWCLO_EINVAL;
+  if ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) != 0) return PWCLO_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  pwclo::adam_tick_kernel<<<1, 1, 0, st>>>(state_i, state_f, beta1, beta2);
+  if (n == 0) return pwclo::launch_status();
+  const size_t n4 = (n + 3) / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  const int cap = pwclo::kNumSM * 8;
+  if (blocks > cap) blocks = cap;
+  pwclo::adam_step_dev_kernel<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, state_f, beta1, beta2, eps,
+                                                      weight_decay, grad_scale);
+  return pwclo::launch_status();
+}
 
 PWCLO_API int pwclo_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int step,
                               float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,

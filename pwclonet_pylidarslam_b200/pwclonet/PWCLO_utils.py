@@ -7,8 +7,10 @@ import torch
 def inv_q(q, device=None, scalar_last: bool = False):
     """q^-1 = conj(q) / (|q|^2 + 1e-10); q [B,4]"""
     q_2 = torch.sum(q * q, dim=-1, keepdim=True) + 1e-10
-    sign = torch.tensor([1.0, -1.0, -1.0, -1.0], device=q.device, dtype=q.dtype)
-    return q * sign / q_2
+    # conj(q) built on the device (a host-side constant would be a pageable H2D copy: not CUDA-graph capturable);
+    # q * 1 and q * -1 are exact, so this equals the reference's q * [1,-1,-1,-1]
+    conj = torch.cat((q[..., :1], -q[..., 1:]), dim=-1)
+    return conj / q_2
 
 
 def _hamilton(a, b):

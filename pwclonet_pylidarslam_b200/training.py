@@ -243,29 +243,52 @@ def all_reduce_gradients(arena: FlatArena):
 
 
 class FlatAdam:
-    """torch.optim.Adam semantics (L2 weight decay in the gradient, bias correction) on a FlatArena;
-    one `pwclo_adam_step` launch per step.  state_dict()/load_state_dict() use torch.optim.Adam's
-    layout so that checkpoints move between this trainer and the reference's (trainer.py:884)."""
+    """torch.optim.Adam semantics (L2 weight decay in the gradient, bias correction) on a FlatArena; one
+    `pwclo_adam_step_dev` call per step.  The step counter and the learning rate live in device memory, so a
+    captured CUDA graph of the step stays valid across steps and learning-rate changes.
+    state_dict()/load_state_dict() use torch.optim.Adam's layout so that checkpoints move between this trainer
+    and the reference's (trainer.py:884)."""
 
     def __init__(self, arena: FlatArena, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         if not arena.param.is_cuda:
             raise RuntimeError("FlatAdam needs CUDA parameters (there is no CPU path)")
-        self.arena, self.lr, self.betas, self.eps, self.weight_decay = arena, float(lr), tuple(betas), float(eps), float(weight_decay)
+        self.arena, self.betas, self.eps, self.weight_decay = arena, tuple(betas), float(eps), float(weight_decay)
         self.initial_lr = float(lr)
         self.exp_avg = torch.zeros_like(arena.param)
         self.exp_avg_sq = torch.zeros_like(arena.param)
-        self.steps = 0
+        dev = arena.param.device
+        self._state_i = torch.zeros(4, dtype=torch.int32, device=dev)       # [0] = completed steps
+        self._state_f = torch.zeros(4, dtype=torch.float32, device=dev)     # [0] = lr, [1..2] = per-step scratch
+        self._lr = None
+        self.lr = float(lr)
+
+    @property
+    def lr(self):
+        return self._lr
+
+    @lr.setter
+    def lr(self, value):
+        self._lr = float(value)
+        self._state_f[0:1].fill_(self._lr)          # stream-ordered: takes effect from the next (replayed) step
+
+    @property
+    def steps(self):
+        return int(self._state_i[0])                 # device -> host read; not on the step path
+
+    @steps.setter
+    def steps(self, value):
+        self._state_i[0:1].fill_(int(value))
 
     def zero_grad(self, set_to_none=False):
         self.arena.zero_grad()
 
     def step(self, grad_scale=1.0):
         a = self.arena
-        self.steps += 1
         with torch.cuda.device(a.param.device):
-            _lib.check(_lib.lib().pwclo_adam_step(_p(a.param), _p(a.grad), _p(self.exp_avg), _p(self.exp_avg_sq), a.numel,
-                                                  self.steps, self.lr, self.betas[0], self.betas[1], self.eps,
-                                                  self.weight_decay, float(grad_scale), _lib.stream_ptr()), "adam_step")
+            _lib.check(_lib.lib().pwclo_adam_step_dev(_p(a.param), _p(a.grad), _p(self.exp_avg), _p(self.exp_avg_sq), a.numel,
+                                                      _p(self._state_i), _p(self._state_f), self.betas[0], self.betas[1],
+                                                      self.eps, self.weight_decay, float(grad_scale), _lib.stream_ptr()),
+                       "adam_step")
 
     @property
     def param_groups(self):
@@ -273,12 +296,13 @@ class FlatAdam:
 
     def state_dict(self):
         state, groups, k = {}, [], 0
+        steps = self.steps
         m, v = self.arena.views(self.exp_avg), self.arena.views(self.exp_avg_sq)
         for g in self.arena.groups:
             ids = list(range(k, k + len(g)))
             for i in ids:
-                if self.steps:
-                    state[i] = {"step": torch.tensor(float(self.steps)), "exp_avg": m[i].clone(), "exp_avg_sq": v[i].clone()}
+                if steps:
+                    state[i] = {"step": torch.tensor(float(steps)), "exp_avg": m[i].clone(), "exp_avg_sq": v[i].clone()}
             groups.append({"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
                            "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
                            "differentiable": False, "fused": None, "initial_lr": self.initial_lr, "params": ids})
@@ -375,6 +399,7 @@ class PWCLONetTrainer:
         self.eval_iter = 0
         self.best = None
         self._average_train_loss = None
+        self._graph = None
         self.broadcast_parameters()
 
     # ---- data-parallel plumbing
@@ -392,16 +417,61 @@ class PWCLONetTrainer:
         loss, log = self.loss_module_(pred, gt)
         return loss, log, pred
 
-    def train_step(self, batch):
-        self.prediction_module_.train()
-        self.loss_module_.train()
+    def _step_body(self, batch):
         self._optimizer.zero_grad()
         loss, log, pred = self.pred_loss_forward_pass(batch)
         loss.backward()
         scale = all_reduce_gradients(self.arena)
         self._optimizer.step(grad_scale=scale)
-        self.train_iter += 1
         return loss.detach(), log, pred.detach()
+
+    def train_step(self, batch):
+        self.prediction_module_.train()
+        self.loss_module_.train()
+        out = self._step_body(batch)
+        self.train_iter += 1
+        return out
+
+    # ---- the whole step as ONE CUDA graph (the eager step is ~2 500 launches and bound by the host)
+    def capture(self, batch, warmup=3):
+        """Capture zero_grad -> forward -> loss -> backward -> all-reduce -> Adam for batches shaped like
+        `batch` (its first four entries are copied into static buffers).  The `warmup` eager steps it runs first
+        ARE training steps.  The graph stays valid across steps and learning-rate changes (step counter and lr
+        live in device memory); it is dropped when the BN momentum changes (a captured scalar) or on train(False)."""
+        self.prediction_module_.train()
+        self.loss_module_.train()
+        self._static_batch = [b.to(self.device).clone() if torch.is_tensor(b) else b for b in batch[:4]]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._step_body(self._static_batch)
+                self.train_iter += 1
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_out = self._step_body(self._static_batch)
+        self.train_iter += 1                          # capture executes nothing, but the step below replays it once
+        self._graph.replay()
+        self._graph_momentum = self._bn_scheduler.last_momentum
+        return self._static_out
+
+    def train_step_graphed(self, batch):
+        """copy the batch into the static buffers and replay the captured step; returns the (static) loss, log
+        and prediction tensors, valid until the next replay"""
+        if getattr(self, "_graph", None) is None:
+            return self.capture(batch)
+        for dst, src in zip(self._static_batch, batch):
+            if torch.is_tensor(dst):
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        self.train_iter += 1
+        return self._static_out
+
+    def drop_graph(self):
+        self._graph = None
+        self._static_out = None
 
     def train_epoch(self, batches):
         """`batches`: iterable of collated batches already on the device (or host tensors, which are
@@ -428,6 +498,8 @@ class PWCLONetTrainer:
         else:
             self._optimizer.lr = exponential_lr(c.optimizer_learning_rate, e, c.optimizer_scheduler_decay, c.scheduler_decay_clip)
         self._bn_scheduler.step(self.num_epochs)
+        if getattr(self, "_graph", None) is not None and self._bn_scheduler.last_momentum != self._graph_momentum:
+            self.drop_graph()                         # BN momentum is a captured scalar: re-capture on the next step
         self.num_epochs = e
 
     # ---- checkpoints (trainer.py:840-907)
