@@ -17,6 +17,7 @@ import ctypes
 import numpy as np
 import torch
 
+import contextlib
 import os
 
 from . import _ext, _lib, tc_pack
@@ -189,6 +190,14 @@ class FusedPWCLONet:
         self.launches = 0
         self.verbose_timeline = False
         self.timeline = None     # when a list: (kernel name, start event, end event) per launch
+        # Optional (PWCLO_OVERLAP=1): everything that depends on coordinates only (the FPS chain, the gathers and every
+        # kNN search except the two per level against the pose-warped cloud) on a second stream, ahead of the layer
+        # kernels that consume it.  Measured on the B200: 7.49 ms per 64 pairs against 7.31 ms on one stream -- every
+        # kernel here already fills the machine (the kNN CTAs take 1024 threads x 63 registers, nothing co-resides),
+        # so the streams only interleave whole kernels and the geometry chain, which is the critical path, loses SMs
+        # to the layers.  Off by default.
+        self.overlap = os.environ.get("PWCLO_OVERLAP", "0") == "1"
+        self._side = torch.cuda.Stream(device=dev) if self.overlap else None
 
     # ------------------------------------------------------------------ thin launch helpers
     def _call(self, name, *args, note="", work=(0, 0)):
@@ -337,27 +346,56 @@ class FusedPWCLONet:
         B = xyz_f1.shape[0]
         self._sorted = {}          # (data_ptr, clouds, points) -> sorted kNN workspace, valid for this forward only
         with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            side = self._side if self.overlap else None
+            geo = contextlib.nullcontext() if side is None else torch.cuda.stream(side)
+
+            def mark():
+                """event after the geometry work issued so far (None when everything runs on one stream)"""
+                if side is None:
+                    return None
+                ev = torch.cuda.Event()
+                ev.record(side)
+                return ev
+
+            def need(ev):
+                if ev is not None:
+                    main.wait_event(ev)
+
             # siamese pyramid: both frames share the weights -> one batch of 2B clouds per level
             xyz = self.to_point_major(torch.cat((xyz_f1, xyz_f2), dim=0).float())
-            xs, fs, lvl_idx = [xyz], [None], []
-            for l, (npoint, k) in enumerate(self.LEVELS):
-                fidx = self.fps(xs[-1], npoint)
-                new_xyz = self.gather3(xs[-1], fidx)
-                idx = self.knn(xs[-1], new_xyz, k, keep_sorted=l >= 1)      # levels 1-3 are searched again below
-                feats = self.set_conv(f"psa_{l + 1}.mlp_module", xs[-1], fs[-1], new_xyz, idx)
-                lvl_idx.append((fidx, idx))
-                xs.append(new_xyz)
-                fs.append(feats)
-            X1 = [None] + [x[:B] for x in xs[1:]]
-            X2 = [None] + [x[B:] for x in xs[1:]]
+            if side is not None:
+                side.wait_stream(main)      # inputs are ready; also orders this forward's geometry after the previous forward
+            xs, lvl_idx, lvl_ev = [xyz], [], []
+            with geo:
+                for l, (npoint, k) in enumerate(self.LEVELS):
+                    fidx = self.fps(xs[-1], npoint)
+                    new_xyz = self.gather3(xs[-1], fidx)
+                    idx = self.knn(xs[-1], new_xyz, k, keep_sorted=l >= 1)      # levels 1-3 are searched again below
+                    lvl_idx.append((fidx, idx))
+                    lvl_ev.append(mark())
+                    xs.append(new_xyz)
+                X1 = [None] + [x[:B] for x in xs[1:]]
+                X2 = [None] + [x[B:] for x in xs[1:]]
+                # the remaining coordinate-only searches: coarse cost volume (level 3) and the three set-upconvs
+                idx_q3 = self.knn(X2[3], X1[3], 32)
+                idx_s3 = self.knn(X1[3], X1[3], 4)
+                ev_cv3 = mark()
+                up_idx, up_ev = {}, {}
+                for l in (3, 2, 1):
+                    up_idx[l] = self.knn(X1[l + 1], X1[l], 8)
+                    up_ev[l] = mark()
+            fs = [None]
+            for l in range(len(self.LEVELS)):
+                need(lvl_ev[l])
+                fs.append(self.set_conv(f"psa_{l + 1}.mlp_module", xs[l], fs[-1], xs[l + 1], lvl_idx[l][1]))
             F1 = [None] + [f[:B] for f in fs[1:]]
             F2 = [None] + [f[B:] for f in fs[1:]]
             pose = self._new(B, 4, 7)
 
             # coarse cost volume at level 3 + flow feature encoding (PW/pwclo_net.py:162-167)
-            idx_q = self.knn(X2[3], X1[3], 32)
-            idx_s = self.knn(X1[3], X1[3], 4)
-            emb, _ = self.cost_volume("cost_volume", X1[3], F1[3], X2[3], F2[3], idx_q, idx_s)
+            need(ev_cv3)
+            emb, _ = self.cost_volume("cost_volume", X1[3], F1[3], X2[3], F2[3], idx_q3, idx_s3)
             # flow_feature_encoding re-runs FPS + kNN on xyz1 of level 3: identical to psa_4's (frame 1)
             emb4 = self.set_conv("flow_feature_encoding.mlp_module", X1[3], emb, X1[4], lvl_idx[3][1][:B])
             mask4 = self.pointwise("l4_flow_predictor.mlp_convs", [F1[4], emb4])
@@ -371,10 +409,10 @@ class FusedPWCLONet:
             emb_prev, mask_prev = emb4, mask4
             for l in (3, 2, 1):
                 p = f"pose_warp_refinement_{l}"
-                up_idx = self.knn(X1[l + 1], X1[l], 8)
-                m_f = self.set_conv(f"{p}.setupconv_features.mlp", X1[l + 1], emb_prev, X1[l], up_idx)
+                need(up_ev[l])
+                m_f = self.set_conv(f"{p}.setupconv_features.mlp", X1[l + 1], emb_prev, X1[l], up_idx[l])
                 cf = self.pointwise(f"{p}.setupconv_features.post_mlp", [m_f, F1[l]])
-                m_m = self.set_conv(f"{p}.setupconv_mask.mlp", X1[l + 1], mask_prev, X1[l], up_idx)
+                m_m = self.set_conv(f"{p}.setupconv_mask.mlp", X1[l + 1], mask_prev, X1[l], up_idx[l])
                 cm = self.pointwise(f"{p}.setupconv_mask.post_mlp", [m_m, F1[l]])
                 idx_q, warped = self.knn(X2[l], X1[l], 6, warp_qt=qt)           # pose warp fused into the search
                 idx_s = self.knn(warped, warped, 4)
@@ -387,5 +425,7 @@ class FusedPWCLONet:
                                   f"pwr{l}.emb": ef, f"pwr{l}.mask": em, f"pwr{l}.qt": qt, f"pwr{l}.idx_q": idx_q,
                                   f"pwr{l}.idx_s": idx_s})
                 emb_prev, mask_prev = ef, em
+            if side is not None:
+                main.wait_stream(side)
         self._sorted = {}
         return pose, mask_prev.permute(0, 2, 1), X1[1]
