@@ -87,6 +87,7 @@ __device__ __forceinline__ unsigned point_key(int i, unsigned scan, uint2 pkey) 
 }
 
 // exclusive scan of one value per thread over the CTA; returns the exclusive prefix, *total = CTA sum
+template <int T>
 __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* warp_tot, unsigned* total) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned incl = v;
@@ -100,7 +101,7 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* w
   __syncthreads();
   unsigned before = 0, sum = 0;
 #pragma unroll
-  for (int w = 0; w < kPrepThreads / 32; ++w) {
+  for (int w = 0; w < T / 32; ++w) {
     const unsigned c = warp_tot[w];
     before += w < warp ? c : 0u;
     sum += c;
@@ -109,22 +110,25 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* w
   return before + incl - v;
 }
 
-// exclusive-scan the 1024-bin histogram (2 bins per thread), write the bin starts and locate the bin in which
-// the `want`-th smallest key lies
+// exclusive-scan the 1024-bin histogram (kPrepBins / T bins per thread), write the bin starts and locate the bin
+// in which the `want`-th smallest key lies
+template <int T>
 __device__ void scan_locate(const unsigned* hist, unsigned* starts, unsigned* warp_tot, int want_i, PrepCtl* ctl) {
+  constexpr int PER = kPrepBins / T;
+  static_assert(PER == 1 || PER == 2, "one or two bins per thread");
   const int tid = threadIdx.x;
-  const unsigned c0 = hist[2 * tid], c1 = hist[2 * tid + 1];
+  const unsigned c0 = hist[PER * tid], c1 = PER == 2 ? hist[PER * tid + 1] : 0u;
   if (tid == 0) ctl->bstar = kPrepBins;
   unsigned total;
   const unsigned mine = c0 + c1;
-  const unsigned excl = block_exclusive_scan(mine, warp_tot, &total);      // (its barriers order the bstar reset)
-  starts[2 * tid] = excl;
-  starts[2 * tid + 1] = excl + c0;
-  if (tid == kPrepThreads - 1) { starts[kPrepBins] = total; ctl->total = (int)total; }
+  const unsigned excl = block_exclusive_scan<T>(mine, warp_tot, &total);   // (its barriers order the bstar reset)
+  starts[PER * tid] = excl;
+  if (PER == 2) starts[PER * tid + 1] = excl + c0;
+  if (tid == T - 1) { starts[kPrepBins] = total; ctl->total = (int)total; }
   const unsigned want = (unsigned)want_i;
   if (excl < want && excl + mine >= want) {                  // exactly one thread when there are >= want keys
-    if (excl + c0 >= want) { ctl->bstar = 2 * tid; ctl->below = (int)excl; ctl->bpop = (int)c0; }
-    else { ctl->bstar = 2 * tid + 1; ctl->below = (int)(excl + c0); ctl->bpop = (int)c1; }
+    if (excl + c0 >= want) { ctl->bstar = PER * tid; ctl->below = (int)excl; ctl->bpop = (int)c0; }
+    else { ctl->bstar = PER * tid + 1; ctl->below = (int)(excl + c0); ctl->bpop = (int)c1; }
   }
   __syncthreads();
 }
@@ -187,10 +191,11 @@ scan_keys_kernel(const float4* __restrict__ raw, const long long* __restrict__ o
 constexpr int kPrepIdxBits = 22;
 constexpr unsigned kPrepIdxMask = (1u << kPrepIdxBits) - 1u;
 constexpr int kPrepCandSlack = 2048;     // candidates beyond npoints (expected M/1024)
+constexpr int kSelThreads = 1024;        // select kernel: one CTA per scan, latency bound -> as many threads as fit
 
 // ---------------------------------------------------------------------------------------------------------------
 // launch 2: one CTA per scan selects, orders, gathers
-__global__ void __launch_bounds__(kPrepThreads, 1)
+__global__ void __launch_bounds__(kSelThreads, 1)
 scan_select_kernel(const float4* __restrict__ raw, const long long* __restrict__ offsets, const double* __restrict__ Tr,
                    int tr_per_scan, const double* __restrict__ post, unsigned seed_lo, unsigned seed_hi, int npoints,
                    const unsigned short* __restrict__ pref, const unsigned* __restrict__ ghist, float* __restrict__ out,
@@ -201,7 +206,7 @@ scan_select_kernel(const float4* __restrict__ raw, const long long* __restrict__
   unsigned long long* list = reinterpret_cast<unsigned long long*>(starts + kPrepBins + 2);   // [npoints + kPrepBoundaryCap]
   unsigned* cand = reinterpret_cast<unsigned*>(list + npoints + kPrepBoundaryCap);            // [npoints + kPrepCandSlack]
   __shared__ PrepCtl ctl;
-  __shared__ unsigned warp_tot[kPrepThreads / 32];
+  __shared__ unsigned warp_tot[kSelThreads / 32];
   __shared__ double sT[12], sP[12];
   const int list_cap = npoints + kPrepBoundaryCap, cand_cap = npoints + kPrepCandSlack;
   const int scan = blockIdx.x;
@@ -215,7 +220,7 @@ scan_select_kernel(const float4* __restrict__ raw, const long long* __restrict__
 
   {  // coarse histogram of the scan = sum of the streaming CTAs' histograms
     const unsigned* gh = ghist + (size_t)scan * kPrepSplit * kPrepBins;
-    for (int b = tid; b < kPrepBins; b += kPrepThreads) {
+    for (int b = tid; b < kPrepBins; b += kSelThreads) {
       unsigned c = 0;
 #pragma unroll
       for (int r = 0; r < kPrepSplit; ++r) c += gh[r * kPrepBins + b];
@@ -228,7 +233,7 @@ scan_select_kernel(const float4* __restrict__ raw, const long long* __restrict__
   }
   if (tid == 0) ctl.ncand = 0;
   __syncthreads();
-  scan_locate(hist, starts, warp_tot, npoints, &ctl);
+  scan_locate<kSelThreads>(hist, starts, warp_tot, npoints, &ctl);
   const int cstar = ctl.bstar;
   const int M = ctl.total;
   const bool short_mode = cstar == kPrepBins || too_big;   // fewer survivors than npoints: keep them all, in index order
@@ -240,7 +245,7 @@ scan_select_kernel(const float4* __restrict__ raw, const long long* __restrict__
     // Re-bin exactly those over [0, R) so that a bin holds ~npoints/1024 keys whatever the survivor count is, and
     // compact them (one shared-memory atomic per warp step).
     const unsigned R = (unsigned)(cstar + 1) << (15 - kPrepBinBits);
-    for (int b = tid; b < kPrepBins; b += kPrepThreads) hist[b] = 0;
+    for (int b = tid; b < kPrepBins; b += kSelThreads) hist[b] = 0;
     __syncthreads();
     // 8 prefixes per 16-byte load (aligned on the whole buffer: the first / last load of a scan may straddle its
     // neighbours and is masked), 4 loads in flight per thread
@@ -248,16 +253,16 @@ scan_select_kernel(const float4* __restrict__ raw, const long long* __restrict__
     const uint4* pv = reinterpret_cast<const uint4*>(pref + a0);
     const int nvec = (int)((base + n - a0 + 7) >> 3);
     const int shift = (int)(base - a0);
-    for (int v0 = 0; v0 < nvec; v0 += 4 * kPrepThreads) {
+    for (int v0 = 0; v0 < nvec; v0 += 4 * kSelThreads) {
       uint4 q[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int v = v0 + u * kPrepThreads + tid;
+        const int v = v0 + u * kSelThreads + tid;
         q[u] = v < nvec ? __ldg(pv + v) : make_uint4(~0u, ~0u, ~0u, ~0u);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int i_first = ((v0 + u * kPrepThreads + tid) << 3) - shift;          // scan index of the first of 8
+        const int i_first = ((v0 + u * kSelThreads + tid) << 3) - shift;          // scan index of the first of 8
         const unsigned w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
         unsigned cmask = 0;
 #pragma unroll
@@ -294,12 +299,12 @@ scan_select_kernel(const float4* __restrict__ raw, const long long* __restrict__
       }
     }
     __syncthreads();
-    scan_locate(hist, starts, warp_tot, npoints, &ctl);
+    scan_locate<kSelThreads>(hist, starts, warp_tot, npoints, &ctl);
     const int bstar = ctl.bstar, below = ctl.below, bpop = ctl.bpop;
     const int ncand = min(ctl.ncand, cand_cap);
     const bool overflow = ctl.ncand > cand_cap || bpop > kPrepBoundaryCap;
     // counting sort by fine bin, with the full keys (dense: every thread has work)
-    for (int c = tid; c < ncand; c += kPrepThreads) {
+    for (int c = tid; c < ncand; c += kSelThreads) {
       const unsigned e = cand[c];
       const unsigned bin = e >> kPrepIdxBits;
       if (bin > (unsigned)bstar) continue;
@@ -312,12 +317,12 @@ scan_select_kernel(const float4* __restrict__ raw, const long long* __restrict__
     if (tid == 0 && survivors) survivors[scan] = overflow ? -1 : M;
     // rank inside the bin = final position; gather, transform, write -- 4 entries per thread step so that the four
     // gathers are in flight together
-    for (int j0 = 0; j0 < filled; j0 += 4 * kPrepThreads) {
+    for (int j0 = 0; j0 < filled; j0 += 4 * kSelThreads) {
       int pos[4], idx[4];
       float4 p[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int j = j0 + u * kPrepThreads + tid;
+        const int j = j0 + u * kSelThreads + tid;
         pos[u] = -1;
         idx[u] = 0;
         if (j < filled) {
@@ -349,11 +354,11 @@ scan_select_kernel(const float4* __restrict__ raw, const long long* __restrict__
   // ---- fewer survivors than npoints (rare): all of them in ascending index, then draws with replacement
   {
     unsigned running = 0;
-    for (int i0 = 0; i0 < n && !too_big; i0 += kPrepThreads) {
+    for (int i0 = 0; i0 < n && !too_big; i0 += kSelThreads) {
       const int i = i0 + tid;
       const bool keep = i < n && pf[i] != kPrepRejected;
       unsigned total;
-      const unsigned excl = block_exclusive_scan(keep ? 1u : 0u, warp_tot, &total);
+      const unsigned excl = block_exclusive_scan<kSelThreads>(keep ? 1u : 0u, warp_tot, &total);
       if (keep && running + excl < (unsigned)list_cap) list[running + excl] = (unsigned long long)(unsigned)i;
       running += total;
     }
@@ -361,7 +366,7 @@ scan_select_kernel(const float4* __restrict__ raw, const long long* __restrict__
     have = too_big ? 0 : min(M, list_cap);
     if (tid == 0 && survivors) survivors[scan] = too_big ? -1 : M;
   }
-  for (int j = tid; j < npoints; j += kPrepThreads) {
+  for (int j = tid; j < npoints; j += kSelThreads) {
     int idx;
     if (j < have) {
       idx = (int)(unsigned)list[j];
@@ -422,7 +427,7 @@ PWCLO_API int pwclo_prepare_scans(const float* raw, const long long* offsets, in
                                                                        tr_per_scan ? 1 : 0, slo, shi, pref, ghist);
   int rc = launch_status();
   if (rc) return rc;
-  scan_select_kernel<<<nscan, kPrepThreads, smem, st>>>(reinterpret_cast<const float4*>(raw), offsets, Tr, tr_per_scan ? 1 : 0,
+  scan_select_kernel<<<nscan, kSelThreads, smem, st>>>(reinterpret_cast<const float4*>(raw), offsets, Tr, tr_per_scan ? 1 : 0,
                                                         post, slo, shi, npoints, pref, ghist, out, sel_idx, survivors);
   return launch_status();
 }
