@@ -223,6 +223,19 @@ int pwclo_adam_step(float *param, const float *grad, float *exp_avg, float *exp_
 int pwclo_adam_step_dev(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, size_t n,
                         int32_t *state_i, float *state_f, float beta1, float beta2, float eps,
                         float weight_decay, float grad_scale, void *stream);
+/* Train-mode BatchNorm + ReLU of a shared-MLP layer (P2/pytorch_utils.py:86-167: nn.BatchNorm2d(eps) over
+ * (B, S, K) followed by ReLU), forward and backward, two launches each.  x, y, dy, dx: [B, C, HW] contiguous.
+ * Forward: batch mean / biased variance per channel (double accumulation), running statistics updated as
+ * nn.BatchNorm does (momentum, unbiased variance; pass NULL for both to skip), save_mean / save_invstd [C] for
+ * the backward.  Backward: dx, dgamma [C], dbeta [C] (overwritten) from x, dy (the ReLU mask is recomputed from x).
+ * workspace: pwclo_bn_relu_workspace_bytes(B, C, HW) bytes, 8-byte aligned. */
+size_t pwclo_bn_relu_workspace_bytes(int B, int C, int HW);
+int pwclo_bn_relu_train_fwd(const float *x, const float *gamma, const float *beta, int B, int C, int HW,
+                            float eps, float momentum, float *running_mean, float *running_var,
+                            float *y, float *save_mean, float *save_invstd, void *workspace, void *stream);
+int pwclo_bn_relu_train_bwd(const float *x, const float *dy, const float *gamma, const float *beta,
+                            const float *save_mean, const float *save_invstd, int B, int C, int HW,
+                            float *dx, float *dgamma, float *dbeta, void *workspace, void *stream);
 
 /* ---- input pipeline ----------------------------------------------------------- */
 

@@ -53,6 +53,8 @@ SIGNATURES = {
     "pwclo_accumulate_poses": [_vp, _i, _vp, _vp, _vp],
     "pwclo_adam_step": [_vp, _vp, _vp, _vp, ctypes.c_size_t, _i, _f, _f, _f, _f, _f, _f, _vp],
     "pwclo_adam_step_dev": [_vp, _vp, _vp, _vp, ctypes.c_size_t, _vp, _vp, _f, _f, _f, _f, _f, _vp],
+    "pwclo_bn_relu_train_fwd": [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pwclo_bn_relu_train_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pwclo_pose_loss": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
 }
 
@@ -75,6 +77,8 @@ def lib():
             fn.restype = ctypes.c_int
         L.pwclo_knn_workspace_bytes.argtypes = [_i, _i, _i]
         L.pwclo_knn_workspace_bytes.restype = ctypes.c_size_t
+        L.pwclo_bn_relu_workspace_bytes.argtypes = [_i, _i, _i]
+        L.pwclo_bn_relu_workspace_bytes.restype = ctypes.c_size_t
         L.pwclo_prepare_scans_workspace_bytes.argtypes = [ctypes.c_longlong, _i]
         L.pwclo_prepare_scans_workspace_bytes.restype = ctypes.c_size_t
         L.pwclo_version.restype = ctypes.c_char_p

@@ -6,6 +6,8 @@ nn.Module wrappers whose *parameter names* define the checkpoint layout (SURVEY 
 """
 from typing import List
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -18,6 +20,55 @@ def knn_point(nsample, xyz, new_xyz):
     "dist" output is overwritten by the indices, :46-47) and so do we."""
     idx = _ext.knn(xyz.contiguous(), new_xyz.contiguous(), nsample)
     return idx, idx
+
+
+class FusedBNReLUTrain(torch.autograd.Function):
+    """Train-mode BatchNorm (batch statistics, running-statistics update) + ReLU of one shared-MLP layer on the
+    sm_100a kernels (`pwclo_bn_relu_train_fwd/_bwd`): what nn.BatchNorm2d / nn.BatchNorm1d followed by nn.ReLU
+    compute (P2/pytorch_utils.py:86-167), in two launches per direction instead of cuDNN's batch norm plus separate
+    ReLU kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps):
+        import ctypes
+        from . import _lib
+        x = x.contiguous()
+        B, C = x.shape[0], x.shape[1]
+        HW = x.numel() // (B * C)
+        L = _lib.lib()
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        ws = torch.empty(L.pwclo_bn_relu_workspace_bytes(B, C, HW) // 8, dtype=torch.float64, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.pwclo_bn_relu_train_fwd(p(x), p(weight), p(bias), B, C, HW, float(eps), float(momentum), p(running_mean),
+                                                 p(running_var), p(y), p(mean), p(invstd), p(ws), _lib.stream_ptr()),
+                       "bn_relu_train_fwd")
+        ctx.save_for_backward(x, weight, bias, mean, invstd)
+        ctx.dims = (B, C, HW)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        import ctypes
+        from . import _lib
+        x, weight, bias, mean, invstd = ctx.saved_tensors
+        B, C, HW = ctx.dims
+        dy = dy.contiguous()
+        L = _lib.lib()
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        dx = torch.empty_like(x)
+        dgamma = torch.empty_like(weight)
+        dbeta = torch.empty_like(bias)
+        ws = torch.empty(L.pwclo_bn_relu_workspace_bytes(B, C, HW) // 8, dtype=torch.float64, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.pwclo_bn_relu_train_bwd(p(x), p(dy), p(weight), p(bias), p(mean), p(invstd), B, C, HW, p(dx), p(dgamma),
+                                                 p(dbeta), p(ws), _lib.stream_ptr()), "bn_relu_train_bwd")
+        return dx, dgamma, dbeta, None, None, None, None
+
+
+FUSED_BN_RELU = os.environ.get("PWCLO_FUSED_BN", "1") != "0"
 
 
 class _BN(nn.Sequential):
@@ -45,6 +96,21 @@ class _Conv(nn.Sequential):
             self.add_module("bn", _BN(out_size, norm))
         if activation is not None:
             self.add_module("activation", activation)
+
+    def forward(self, x):
+        """training on the GPU with BatchNorm + ReLU: conv by torch, then ONE fused BN(train) + ReLU op (same
+        parameters / buffers / state-dict keys: the nn.BatchNorm module stays the owner of its tensors)"""
+        bn = getattr(self, "bn", None)
+        act = getattr(self, "activation", None)
+        if (FUSED_BN_RELU and self.training and bn is not None and isinstance(act, nn.ReLU) and x.is_cuda
+                and x.dtype == torch.float32):
+            norm = bn[0]
+            if norm.track_running_stats and norm.momentum is not None and norm.affine:
+                y = self.conv(x)
+                norm.num_batches_tracked.add_(1)
+                return FusedBNReLUTrain.apply(y, norm.weight, norm.bias, norm.running_mean, norm.running_var, norm.momentum,
+                                              norm.eps)
+        return super().forward(x)
 
 
 class Conv2d(_Conv):

@@ -205,3 +205,30 @@ def test_graphed_step_equals_eager_step(cuda, monkeypatch):
     b.train_step_graphed(batch)
     d1 = float((b.arena.param - p0).abs().max())
     assert 0 < d1 < 1e-2
+
+
+@pytest.mark.parametrize("shape", [(4, 16, 512, 32), (16, 8, 2048, 32), (3, 64, 37, 5), (2, 128, 64), (8, 256, 1, 1), (2, 7, 1000)])
+def test_fused_bn_relu_train_matches_torch(cuda, shape):
+    """pwclo_bn_relu_train_fwd/_bwd against nn.BatchNorm (train mode, cuDNN / ATen) + ReLU on the same GPU: outputs,
+    running statistics and all three gradients.  fp32 with double-accumulated statistics: 2e-5 relative to the
+    largest entry (torch accumulates in fp32)."""
+    from pwclonet_pylidarslam_b200.pytorch_utils import FusedBNReLUTrain
+    g = torch.Generator(device=cuda).manual_seed(sum(shape))
+    C = shape[1]
+    x = (torch.randn(shape, device=cuda, generator=g) * 2.0 + 0.7).requires_grad_(True)
+    w = (torch.rand(C, device=cuda, generator=g) + 0.5).requires_grad_(True)
+    b = (torch.randn(C, device=cuda, generator=g) * 0.3).requires_grad_(True)
+    up = torch.randn(shape, device=cuda, generator=g)
+    rm0, rv0 = torch.randn(C, device=cuda, generator=g) * 0.1, torch.rand(C, device=cuda, generator=g) + 0.5
+    rm, rv = rm0.clone(), rv0.clone()
+    y = FusedBNReLUTrain.apply(x, w, b, rm, rv, 0.3, 1e-5)
+    (y * up).sum().backward()
+    got = [y.detach(), x.grad.clone(), w.grad.clone(), b.grad.clone(), rm, rv]
+    x.grad = w.grad = b.grad = None
+    rm2, rv2 = rm0.clone(), rv0.clone()
+    yr = torch.relu(torch.nn.functional.batch_norm(x, rm2, rv2, w, b, True, 0.3, 1e-5))
+    (yr * up).sum().backward()
+    want = [yr.detach(), x.grad, w.grad, b.grad, rm2, rv2]
+    for name, a, r in zip(("y", "dx", "dgamma", "dbeta", "running_mean", "running_var"), got, want):
+        err = float((a - r).abs().max())
+        assert err <= 2e-5 * float(r.abs().max()) + 1e-7, (name, shape, err, float(r.abs().max()))
