@@ -29,12 +29,19 @@ class PointnetSAModulePWCLONet(nn.Module):
         self.mlp_spec = spec
         self.mlp_module = pt_utils.SharedMLP(spec, bn=bn, init=torch.nn.init.xavier_uniform_)
 
-    def forward(self, xyz: torch.Tensor, features: Optional[torch.Tensor]):
+    def geometry(self, xyz: torch.Tensor):
+        """the non-differentiable, coordinates-only part of forward: (FPS indices [B,npoint], new_xyz [B,npoint,3],
+        neighbour indices [B,npoint,nsample]).  A caller that processes several clouds with this module (the two
+        frames of a pair) can compute it for all of them in one batch and hand slices to forward(geom=...)."""
+        fidx = pointnet2_utils.furthest_point_sample(xyz, self.npoint)
+        new_xyz = pointnet2_utils.gather_operation(xyz.transpose(1, 2).contiguous(), fidx).transpose(1, 2).contiguous()
+        _, idx = pt_utils.knn_point(self.nsample, xyz, new_xyz)
+        return fidx, new_xyz, idx
+
+    def forward(self, xyz: torch.Tensor, features: Optional[torch.Tensor], geom=None):
         """xyz (B,N,3), features (B,C,N) or None -> new_xyz (B,npoint,3), new_features (B,C',npoint)"""
         xyz_flipped = xyz.transpose(1, 2).contiguous()
-        fidx = pointnet2_utils.furthest_point_sample(xyz, self.npoint)
-        new_xyz = pointnet2_utils.gather_operation(xyz_flipped, fidx).transpose(1, 2).contiguous()
-        _, idx = pt_utils.knn_point(self.nsample, xyz, new_xyz)
+        fidx, new_xyz, idx = self.geometry(xyz) if geom is None else geom
         grouped_xyz = pointnet2_utils.grouping_operation(xyz_flipped, idx)
         xyz_diff = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
         if features is not None:

@@ -133,17 +133,30 @@ class PWCLONet(nn.Module):
         xyz_f1_t = xyz_f1.permute(0, 2, 1).contiguous()
         xyz_f2_t = xyz_f2.permute(0, 2, 1).contiguous()
         x1, f1, x2, f2 = [xyz_f1_t], [points_f1], [xyz_f2_t], [points_f2]
+        # FPS / gather / kNN depend on coordinates only and are not differentiable: one batch of 2B clouds per level
+        # for both frames (per cloud the same indices as the reference's per-frame calls; with 8 pairs per GPU the
+        # 16384 -> 2048 sampling is a 2047-round chain on 8 CTAs, twice, otherwise).  The layers keep their per-frame
+        # calls: train-mode BatchNorm statistics must be those of one frame's batch, as in the reference.
+        Bp = xyz_f1_t.shape[0]
+        geoms, cur = [], torch.cat((xyz_f1_t, xyz_f2_t), dim=0).detach()
         for psa in (self.psa_1, self.psa_2, self.psa_3, self.psa_4):
-            a, b = psa(x1[-1], f1[-1])
+            g = psa.geometry(cur)
+            geoms.append(g)
+            cur = g[1]
+        for psa, g in zip((self.psa_1, self.psa_2, self.psa_3, self.psa_4), geoms):
+            a, b = psa(x1[-1], f1[-1], geom=tuple(t[:Bp] for t in g))
             x1.append(a), f1.append(b)
-        for psa in (self.psa_1, self.psa_2, self.psa_3, self.psa_4):
-            a, b = psa(x2[-1], f2[-1])
+        for psa, g in zip((self.psa_1, self.psa_2, self.psa_3, self.psa_4), geoms):
+            a, b = psa(x2[-1], f2[-1], geom=tuple(t[Bp:] for t in g))
             x2.append(a), f2.append(b)
         X1 = [None] + [x.permute(0, 2, 1).contiguous() for x in x1[1:]]   # [B,3,S] per level 1..4
         X2 = [None] + [x.permute(0, 2, 1).contiguous() for x in x2[1:]]
 
         flow_embedding = self.cost_volume(X1[3], f1[3], X2[3], f2[3])
-        xyz_f1_4_t, emb_4 = self.flow_feature_encoding(x1[3], flow_embedding)
+        # flow_feature_encoding samples and groups xyz1 of level 3 exactly as psa_4 did for frame 1 (same npoint / nsample)
+        ffe = self.flow_feature_encoding
+        same = ffe.npoint == self.psa_4.npoint and ffe.nsample == self.psa_4.nsample
+        xyz_f1_4_t, emb_4 = ffe(x1[3], flow_embedding, geom=tuple(t[:Bp] for t in geoms[3]) if same else None)
         new_xyz_f1_4 = xyz_f1_4_t.permute(0, 2, 1).contiguous()
         mask_4 = self.l4_flow_predictor(f1[4], emb_4)
         q_4, t_4 = self.pose_calculator_4(emb_4, F.softmax(mask_4, dim=2))
