@@ -8,7 +8,5 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_o
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_list.log 2>&1
-# every kernel of one whole forward, full counter set (no source pages: keeps the report small)
-timeout 900 ncu --set full --clock-control none -k regex:pwclo -s 320 -c 90 -f -o gpurun_out/${TAG}_full_forward \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
+# full-counter captures: tools/ncu_full_forward.sh (kept separate: ~6 GPU-minutes)
 tail -3 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_bench.json | cut -c1-1500
