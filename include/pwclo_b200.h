@@ -257,6 +257,16 @@ int pwclo_prepare_scans(const float *raw, const long long *offsets, int nscan, l
                         const double *Tr, int tr_per_scan, const double *post,
                         unsigned long long seed, int npoints, float *out, int32_t *sel_idx,
                         int32_t *survivors, void *workspace, size_t workspace_bytes, void *stream);
+/* The same with the crop spelled out: a point is dropped when ground_sign * (P[ground_axis] - ground_thr) > 0 or
+ * when |P[near_axis_a]| or |P[near_axis_b]| is not below near_thr.  pwclo_prepare_scans = (1, +1, 1.1, 0, 2, 30.0);
+ * KITTI-360 (slam/dataset/kitti_360_dataset_2.py:113-123: velodyne frame, Tr = identity, comparisons in float32) =
+ * (2, -1, (double)(float)-1.43, 0, 1, (double)(float)near_treshold). */
+int pwclo_prepare_scans_crop(const float *raw, const long long *offsets, int nscan, long long total_points,
+                             const double *Tr, int tr_per_scan, const double *post,
+                             unsigned long long seed, int npoints, int ground_axis, int ground_sign,
+                             double ground_thr, int near_axis_a, int near_axis_b, double near_thr,
+                             float *out, int32_t *sel_idx, int32_t *survivors, void *workspace,
+                             size_t workspace_bytes, void *stream);
 
 /* ---- pose post-processing ------------------------------------------------ */
 

@@ -84,11 +84,25 @@ def affine(T, xyz):
     return np.stack([fma(T[r, 2], z, fma(T[r, 1], y, T[r, 0] * x)) + T[r, 3] for r in range(3)], axis=1)
 
 
-def keep_mask(P):
-    """filter_pcd :151-159 on the transformed float64 points"""
-    not_ground = np.logical_not(P[:, 1] > 1.1)
-    near = np.logical_and(np.logical_and(P[:, 0] < 30, P[:, 0] > -30), np.logical_and(P[:, 2] < 30, P[:, 2] > -30))
-    return np.logical_and(not_ground, near)
+KITTI_ODOMETRY_CROP = (1, +1, 1.1, 0, 2, 30.0)
+
+
+def keep_mask(P, crop=KITTI_ODOMETRY_CROP):
+    """filter_pcd on the transformed float64 points: kitti_odometry_dataset.py:151-159 by default; any crop
+    (ground_axis, ground_sign, ground_thr, near_a, near_b, near_thr), e.g. kitti_360_dataset_2.py:113-123"""
+    ga, gs, gt, a, b, nt = crop
+    ground = P[:, ga] > gt if gs > 0 else P[:, ga] < gt
+    near = np.logical_and(np.logical_and(P[:, a] < nt, P[:, a] > -nt), np.logical_and(P[:, b] < nt, P[:, b] > -nt))
+    return np.logical_and(np.logical_not(ground), near)
+
+
+def reference_mask_kitti360(points_f32, near_treshold=30.0):
+    """the literal reference expression of kitti_360_dataset_2.py:113-123 on the float32 velodyne points, for pinning"""
+    wheel_axis_z = -(1.73 - 0.3)
+    is_ground = points_f32[:, 2] < wheel_axis_z
+    near_x = np.logical_and(points_f32[:, 0] < near_treshold, points_f32[:, 0] > -near_treshold)
+    near_y = np.logical_and(points_f32[:, 1] < near_treshold, points_f32[:, 1] > -near_treshold)
+    return np.logical_and(np.logical_not(is_ground), np.logical_and(near_x, near_y))
 
 
 def select(mask, scan, seed, npoints):
@@ -107,10 +121,10 @@ def select(mask, scan, seed, npoints):
     return ((u * np.uint64(n)) >> np.uint64(32)).astype(np.int32), 0
 
 
-def prepare_scan(raw, Tr, scan, seed, npoints, post=None):
+def prepare_scan(raw, Tr, scan, seed, npoints, post=None, crop=KITTI_ODOMETRY_CROP):
     """raw float32[n,4] -> (float32[npoints,3], int32[npoints] source rows, survivors)"""
     P = affine(Tr, raw[:, :3])
-    sel, M = select(keep_mask(P), scan, seed, npoints)
+    sel, M = select(keep_mask(P, crop), scan, seed, npoints)
     Q = P[sel]
     if post is not None:
         Q = affine(post, Q)

@@ -51,6 +51,8 @@ SIGNATURES = {
                             ctypes.c_size_t, _vp],
     "pwclo_pose_to_matrix": [_vp, _i, _i, _i, _vp, _vp],
     "pwclo_accumulate_poses": [_vp, _i, _vp, _vp, _vp],
+    "pwclo_prepare_scans_crop": [_vp, _vp, _i, ctypes.c_longlong, _vp, _i, _vp, ctypes.c_ulonglong, _i, _i, _i, ctypes.c_double,
+                                 _i, _i, ctypes.c_double, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp],
     "pwclo_adam_step": [_vp, _vp, _vp, _vp, ctypes.c_size_t, _i, _f, _f, _f, _f, _f, _f, _vp],
     "pwclo_adam_step_dev": [_vp, _vp, _vp, _vp, ctypes.c_size_t, _vp, _vp, _f, _f, _f, _f, _f, _vp],
     "pwclo_bn_relu_train_fwd": [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -65,9 +65,21 @@ __device__ __forceinline__ void affine3x4(const double* __restrict__ T, double x
   Z = __dadd_rn(__fma_rn(T[10], z, __fma_rn(T[9], y, __dmul_rn(T[8], x))), T[11]);
 }
 
-__device__ __forceinline__ bool keep_point(double X, double Y, double Z) {
-  // filter_pcd: not (y > 1.1) and -30 < x < 30 and -30 < z < 30   (kitti_odometry_dataset.py:151-159)
-  return !(Y > 1.1) && (X < 30.0) && (X > -30.0) && (Z < 30.0) && (Z > -30.0);
+// filter_pcd of the two datasets the reference trains PWCLO-Net on:
+//   KITTI odometry (kitti_odometry_dataset.py:151-159, camera-style frame): not (y > 1.1) and |x| < 30 and |z| < 30
+//   KITTI-360 (kitti_360_dataset_2.py:113-123, velodyne frame, no Tr):       not (z < -(1.73-0.3)) and |x| < near and |y| < near
+struct CropSpec {
+  int ground_axis, ground_sign;   // reject when sign * (P[axis] - thr) > 0
+  int near_a, near_b;             // keep when |P[a]| < near and |P[b]| < near (strict, both signs, as the reference)
+  double ground_thr, near_thr;
+};
+
+__device__ __forceinline__ bool keep_point(const CropSpec& c, double X, double Y, double Z) {
+  const double g = c.ground_axis == 0 ? X : (c.ground_axis == 1 ? Y : Z);
+  const double a = c.near_a == 0 ? X : (c.near_a == 1 ? Y : Z);
+  const double b = c.near_b == 0 ? X : (c.near_b == 1 ? Y : Z);
+  const bool ground = c.ground_sign > 0 ? (g > c.ground_thr) : (g < c.ground_thr);
+  return !ground && (a < c.near_thr) && (a > -c.near_thr) && (b < c.near_thr) && (b > -c.near_thr);
 }
 
 struct PrepCtl {
@@ -137,7 +149,7 @@ __device__ void scan_locate(const unsigned* hist, unsigned* starts, unsigned* wa
 // launch 1: stream every scan point once
 __global__ void __launch_bounds__(kPrepThreads, 2)
 scan_keys_kernel(const float4* __restrict__ raw, const long long* __restrict__ offsets, const double* __restrict__ Tr,
-                 int tr_per_scan, unsigned seed_lo, unsigned seed_hi, unsigned short* __restrict__ pref,
+                 int tr_per_scan, CropSpec crop, unsigned seed_lo, unsigned seed_hi, unsigned short* __restrict__ pref,
                  unsigned* __restrict__ ghist) {
   __shared__ unsigned hist[kPrepBins];
   __shared__ double sT[12];
@@ -172,7 +184,7 @@ scan_keys_kernel(const float4* __restrict__ raw, const long long* __restrict__ o
         unsigned short v = kPrepRejected;
         double X, Y, Z;
         affine3x4(sT, (double)p[k].x, (double)p[k].y, (double)p[k].z, X, Y, Z);
-        if (keep_point(X, Y, Z)) {
+        if (keep_point(crop, X, Y, Z)) {
           const unsigned top15 = pick4(r, k) >> 17;              // (key31 = word >> 1) >> 16
           v = (unsigned short)top15;
           atomicAdd(&hist[top15 >> (15 - kPrepBinBits)], 1u);
@@ -404,7 +416,23 @@ PWCLO_API int pwclo_prepare_scans(const float* raw, const long long* offsets, in
                                   const double* Tr, int tr_per_scan, const double* post, unsigned long long seed, int npoints,
                                   float* out, int32_t* sel_idx, int32_t* survivors, void* workspace, size_t workspace_bytes,
                                   void* stream) {
+  // KITTI odometry crop (kitti_odometry_dataset.py:151-159)
+  return pwclo_prepare_scans_crop(raw, offsets, nscan, total_points, Tr, tr_per_scan, post, seed, npoints, 1, +1, 1.1, 0, 2, 30.0,
+                                  out, sel_idx, survivors, workspace, workspace_bytes, stream);
+}
+
+PWCLO_API int pwclo_prepare_scans_crop(const float* raw, const long long* offsets, int nscan, long long total_points,
+                                       const double* Tr, int tr_per_scan, const double* post, unsigned long long seed,
+                                       int npoints, int ground_axis, int ground_sign, double ground_thr, int near_axis_a,
+                                       int near_axis_b, double near_thr, float* out, int32_t* sel_idx, int32_t* survivors,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
   using namespace pwclo;
+  if (ground_axis < 0 || ground_axis > 2 || near_axis_a < 0 || near_axis_a > 2 || near_axis_b < 0 || near_axis_b > 2 ||
+      ground_sign == 0)
+    return PWCLO_EINVAL;
+  CropSpec crop;
+  crop.ground_axis = ground_axis; crop.ground_sign = ground_sign; crop.near_a = near_axis_a; crop.near_b = near_axis_b;
+  crop.ground_thr = ground_thr; crop.near_thr = near_thr;
   if (!raw || !offsets || !Tr || !out || !workspace || nscan < 0 || npoints <= 0 || total_points < 0) return PWCLO_EINVAL;
   if (((uintptr_t)raw & 15) != 0 || ((uintptr_t)workspace & 15) != 0) return PWCLO_EINVAL;
   if (workspace_bytes < pwclo_prepare_scans_workspace_bytes(total_points, nscan)) return PWCLO_EINVAL;
@@ -424,7 +452,7 @@ PWCLO_API int pwclo_prepare_scans(const float* raw, const long long* offsets, in
   const unsigned slo = (unsigned)(seed & 0xffffffffull), shi = (unsigned)(seed >> 32);
   cudaStream_t st = (cudaStream_t)stream;
   scan_keys_kernel<<<dim3(kPrepSplit, nscan, 1), kPrepThreads, 0, st>>>(reinterpret_cast<const float4*>(raw), offsets, Tr,
-                                                                       tr_per_scan ? 1 : 0, slo, shi, pref, ghist);
+                                                                       tr_per_scan ? 1 : 0, crop, slo, shi, pref, ghist);
   int rc = launch_status();
   if (rc) return rc;
   scan_select_kernel<<<nscan, kSelThreads, smem, st>>>(reinterpret_cast<const float4*>(raw), offsets, Tr, tr_per_scan ? 1 : 0,

@@ -38,7 +38,22 @@ def pack_pairs(scans1, scans2, pin=True):
     return pack_scans(seq, pin)
 
 
-def prepare_scans(raw, offsets, Tr, npoints, seed, post=None, max_points=None, return_index=False):
+# crop specifications (ground_axis, ground_sign, ground_thr, near_axis_a, near_axis_b, near_thr), see include/pwclo_b200.h
+KITTI_ODOMETRY_CROP = (1, +1, 1.1, 0, 2, 30.0)                 # kitti_odometry_dataset.py:151-159 (camera-style frame)
+
+
+def kitti360_crop(near_treshold=30.0, velodyne_height=1.73, wheel_axis_height=0.3):
+    """slam/dataset/kitti_360_dataset_2.py:113-123: velodyne frame (pass the identity as Tr), ground = z below the wheel
+    axis, comparisons in float32 -- the thresholds are rounded to float32 so that the float64 comparisons of the kernel
+    decide exactly as the reference's float32 ones do on float32 coordinates."""
+    ground = float(np.float32(-(velodyne_height - wheel_axis_height)))
+    return (2, -1, ground, 0, 1, float(np.float32(near_treshold)))
+
+
+IDENTITY_TR = np.ascontiguousarray(np.eye(4)[:3], np.float64)
+
+
+def prepare_scans(raw, offsets, Tr, npoints, seed, post=None, max_points=None, return_index=False, crop=KITTI_ODOMETRY_CROP):
     """(`max_points` is accepted for compatibility and ignored.)
     raw float32 [total,4] CUDA, offsets int64 [S+1] CUDA, Tr float64 [3,4] (or [S,3,4]) CUDA ->
     clouds float32 [S,npoints,3] (+ int32 [S,npoints] source rows, int32 [S] survivors)."""
@@ -59,7 +74,8 @@ def prepare_scans(raw, offsets, Tr, npoints, seed, post=None, max_points=None, r
     surv = torch.empty((S,), dtype=torch.int32, device=raw.device)
     p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
     with torch.cuda.device(raw.device):
-        _lib.check(L.pwclo_prepare_scans(p(raw), p(offsets), S, total, p(Tr), 1 if per_scan else 0, p(post),
-                                         ctypes.c_ulonglong(int(seed) & (2 ** 64 - 1)), int(npoints), p(out), p(idx), p(surv),
-                                         p(ws), ws.numel(), _lib.stream_ptr()), "prepare_scans")
+        _lib.check(L.pwclo_prepare_scans_crop(p(raw), p(offsets), S, total, p(Tr), 1 if per_scan else 0, p(post),
+                                              ctypes.c_ulonglong(int(seed) & (2 ** 64 - 1)), int(npoints), int(crop[0]),
+                                              int(crop[1]), float(crop[2]), int(crop[3]), int(crop[4]), float(crop[5]),
+                                              p(out), p(idx), p(surv), p(ws), ws.numel(), _lib.stream_ptr()), "prepare_scans")
     return (out, idx, surv) if return_index else out

@@ -52,3 +52,25 @@ def test_forward_gpu_order_vs_port(cuda):
             want, _ = Port(w, sum_order=1).forward(x1, x2)
         te, re_ = C.pose_errors(pose.cpu().numpy(), want.numpy())
         assert te <= C.TOL_TRANSLATION_M and re_ <= C.TOL_ROTATION_RAD, (fused, te, re_)
+
+
+def test_pose_pipeline_equals_direct_forward(cuda):
+    """sharding.PosePipeline (copy of batch i+1 overlapped with the forward of batch i) returns, in order, exactly
+    what the direct calls return"""
+    from pwclonet_pylidarslam_b200 import synthetic as syn
+    from pwclonet_pylidarslam_b200.pwclonet import PWCLONet
+    from pwclonet_pylidarslam_b200.sharding import PosePipeline
+    net = PWCLONet({"device": "cuda:0"}).to(cuda).eval()
+    batches = []
+    for i in range(5):
+        x1, x2, _ = syn.make_batch(300 + 2 * i, 2, 4096)
+        batches.append((torch.from_numpy(x1).pin_memory(), torch.from_numpy(x2).pin_memory()))
+    direct = []
+    with torch.no_grad():
+        for h1, h2 in batches:
+            direct.append(net(h1.to(cuda), None, h2.to(cuda), None)[0].cpu())
+    pipe = PosePipeline(net, 2, 4096)
+    got = [p.clone() for p in pipe.run(iter(batches))]
+    assert len(got) == 5
+    for a, b in zip(got, direct):
+        assert torch.equal(a, b)

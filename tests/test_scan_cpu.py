@@ -73,3 +73,22 @@ def test_short_and_empty_scans():
     assert M == 40 and sel[:40].tolist() == list(range(40)) and set(sel[40:].tolist()) <= set(range(40))
     pts, sel, M = S.prepare_scan(raw[40:], syn.KITTI_TR, 0, 9, 128)
     assert M == 0 and sel.min() >= 0 and sel.max() < 260 and len(set(sel.tolist())) > 60
+
+
+def test_kitti360_crop_equals_reference_expression():
+    """velodyne-frame crop of kitti_360_dataset_2.py:113-123 (float32 comparisons): float32-rounded thresholds make
+    the float64 comparisons of oracle and kernel decide identically, also for coordinates exactly at a threshold"""
+    from pwclonet_pylidarslam_b200 import scan_input
+    raw = syn.make_raw_scan(8)
+    crop = scan_input.kitti360_crop(30.0)
+    thr = np.float32(-(1.73 - 0.3))
+    raw[:50, 2] = thr                                   # exactly on the ground threshold
+    raw[50:100, 2] = np.nextafter(thr, np.float32(-10))
+    raw[100:150, 2] = np.nextafter(thr, np.float32(10))
+    raw[150:170, 0] = np.float32(30.0)
+    P = S.affine(scan_input.IDENTITY_TR, raw[:, :3])
+    np.testing.assert_array_equal(P, raw[:, :3].astype(np.float64))          # identity Tr is exact
+    np.testing.assert_array_equal(S.keep_mask(P, crop), S.reference_mask_kitti360(raw[:, :3], 30.0))
+    pts, sel, M = S.prepare_scan(raw, scan_input.IDENTITY_TR, 0, 3, 16384, crop=crop)
+    assert M == S.reference_mask_kitti360(raw[:, :3]).sum() and pts.shape == (16384, 3)
+    np.testing.assert_array_equal(pts, raw[sel, :3])

@@ -69,6 +69,24 @@ def test_augmentation_transform_and_16384_points(cuda):
     _check(scans, 4096, 5, got, Tr=Tr)
 
 
+def test_kitti360_crop(cuda):
+    """KITTI-360 flavour: velodyne frame, identity Tr, ground below the wheel axis, 16384 points kept"""
+    scans = [syn.make_raw_scan(31), syn.make_raw_scan(32)[:60000]]
+    thr = np.float32(-(1.73 - 0.3))
+    scans[0][:64, 2] = thr
+    scans[0][64:128, 2] = np.nextafter(thr, np.float32(-10))
+    crop = scan_input.kitti360_crop(30.0)
+    buf, off, mx = scan_input.pack_scans(scans)
+    out, idx, surv = scan_input.prepare_scans(buf.to(cuda), off.to(cuda), torch.from_numpy(scan_input.IDENTITY_TR.copy()).to(cuda),
+                                              16384, 77, return_index=True, crop=crop)
+    out, idx, surv = out.cpu().numpy(), idx.cpu().numpy(), surv.cpu().numpy()
+    for s, raw in enumerate(scans):
+        want, sel, M = S.prepare_scan(raw, scan_input.IDENTITY_TR, s, 77, 16384, crop=crop)
+        assert surv[s] == M == S.reference_mask_kitti360(raw[:, :3]).sum()
+        np.testing.assert_array_equal(idx[s], sel)
+        np.testing.assert_array_equal(out[s], want)
+
+
 def test_pipeline_feeds_the_network(cuda):
     """raw scans -> prepare_scans -> PWCLONet fused forward, no host round trip in between"""
     from pwclonet_pylidarslam_b200.pwclonet import PWCLONet
