@@ -223,6 +223,13 @@ int pwclo_adam_step(float *param, const float *grad, float *exp_avg, float *exp_
 int pwclo_adam_step_dev(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, size_t n,
                         int32_t *state_i, float *state_f, float beta1, float beta2, float eps,
                         float weight_decay, float grad_scale, void *stream);
+/* Pose warp for training (PW/PWCLO_utils.py:31-63): out[B,3,N] = q (x) [0, xyz] (x) q^-1 + t, xyz channel-major [B,3,N],
+ * q [B,4] scalar first, t [B,3]; and its gradient: grad_q [B,4], grad_t [B,3] (overwritten), grad_xyz [B,3,N] (NULL =
+ * not needed).  One launch each. */
+int pwclo_warp_fwd(const float *xyz, const float *q, const float *t, int B, int N, float *out, void *stream);
+int pwclo_warp_bwd(const float *xyz, const float *q, const float *grad_out, int B, int N, float *grad_xyz,
+                   float *grad_q, float *grad_t, void *stream);
+
 /* Train-mode BatchNorm + ReLU of a shared-MLP layer (P2/pytorch_utils.py:86-167: nn.BatchNorm2d(eps) over
  * (B, S, K) followed by ReLU), forward and backward, two launches each.  x, y, dy, dx: [B, C, HW] contiguous.
  * Forward: batch mean / biased variance per channel (double accumulation), running statistics updated as

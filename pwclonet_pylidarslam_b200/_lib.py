@@ -57,6 +57,8 @@ SIGNATURES = {
     "pwclo_adam_step_dev": [_vp, _vp, _vp, _vp, ctypes.c_size_t, _vp, _vp, _f, _f, _f, _f, _f, _vp],
     "pwclo_bn_relu_train_fwd": [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pwclo_bn_relu_train_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "pwclo_warp_fwd": [_vp, _vp, _vp, _i, _i, _vp, _vp],
+    "pwclo_warp_bwd": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
     "pwclo_pose_loss": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
 }
 

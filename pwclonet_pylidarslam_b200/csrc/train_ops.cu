@@ -149,6 +149,85 @@ adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
     adam_one(p[i], g[i], m[i], v[i], lr_over_bc1, b1, b2, eps, wd, sqrt_bc2, gscale);
 }
 
+// Pose warp of a cloud, p' = q (x) [0,p] (x) q^-1 + t with q^-1 = conj(q) / (|q|^2 + 1e-10) (PW/PWCLO_utils.py:31-63), as ONE
+// launch forward and ONE backward for training: the reference's torch expression is ~60 element-wise launches forward
+// and ~150 in autograd's replay, three times per step.  xyz / out are channel-major [B,3,N] (the layout the composed
+// path holds), q [B,4] scalar first, t [B,3].  Forward values are op-for-op those of the expression (warp_point).
+// Backward, with s = |q|^2 + 1e-10, q = (w, v), u = (w^2 - v.v) p + 2 (v.p) v + 2 w (v x p) = s (p' - t), g = dL/dp':
+//   dL/dt = sum g          dL/dp = [(w^2 - v.v) g + 2 (v.g) v - 2 w (v x g)] / s
+//   dL/dw = sum [2 w (p.g) + 2 (v x p).g] / s - (u.g) 2 w / s^2
+//   dL/dv = sum [-2 (p.g) v + 2 (v.g) p + 2 (v.p) g + 2 w (p x g)] / s - (u.g) 2 v / s^2
+constexpr int kWarpThreads = 256;
+
+__global__ void __launch_bounds__(kWarpThreads)
+warp_fwd_kernel(const float* __restrict__ xyz, const float* __restrict__ q, const float* __restrict__ t, int N,
+                float* __restrict__ out) {
+  const int b = blockIdx.y;
+  __shared__ float qt[7];
+  if (threadIdx.x < 4) qt[threadIdx.x] = q[b * 4 + threadIdx.x];
+  else if (threadIdx.x < 7) qt[threadIdx.x] = t[b * 3 + threadIdx.x - 4];
+  __syncthreads();
+  const PoseQT P = make_pose(qt);
+  const float* x = xyz + (size_t)b * 3 * N;
+  float* o = out + (size_t)b * 3 * N;
+  for (int n = blockIdx.x * kWarpThreads + threadIdx.x; n < N; n += gridDim.x * kWarpThreads) {
+    float ox, oy, oz;
+    warp_point(P, x[n], x[N + n], x[2 * N + n], ox, oy, oz);
+    o[n] = ox; o[N + n] = oy; o[2 * N + n] = oz;
+  }
+}
+
+__global__ void __launch_bounds__(kWarpThreads)
+warp_bwd_kernel(const float* __restrict__ xyz, const float* __restrict__ q, const float* __restrict__ gout, int N,
+                float* __restrict__ dxyz, float* __restrict__ dq, float* __restrict__ dt) {
+  const int b = blockIdx.x;
+  __shared__ double red[7][kWarpThreads / 32];
+  const double w = q[b * 4 + 0], vx = q[b * 4 + 1], vy = q[b * 4 + 2], vz = q[b * 4 + 3];
+  const double s = w * w + vx * vx + vy * vy + vz * vz + 1e-10;
+  const double ww = w * w - (vx * vx + vy * vy + vz * vz);
+  const float* x = xyz + (size_t)b * 3 * N;
+  const float* g = gout + (size_t)b * 3 * N;
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};     // dw, dvx, dvy, dvz, dtx, dty, dtz
+  for (int n = threadIdx.x; n < N; n += kWarpThreads) {
+    const double px = x[n], py = x[N + n], pz = x[2 * N + n];
+    const double gx = g[n], gy = g[N + n], gz = g[2 * N + n];
+    const double vp = vx * px + vy * py + vz * pz, vg = vx * gx + vy * gy + vz * gz, pg = px * gx + py * gy + pz * gz;
+    // v x p, p x g, v x g
+    const double cx = vy * pz - vz * py, cy = vz * px - vx * pz, cz = vx * py - vy * px;
+    const double hx = py * gz - pz * gy, hy = pz * gx - px * gz, hz = px * gy - py * gx;
+    const double ux = ww * px + 2.0 * vp * vx + 2.0 * w * cx, uy = ww * py + 2.0 * vp * vy + 2.0 * w * cy,
+                 uz = ww * pz + 2.0 * vp * vz + 2.0 * w * cz;
+    const double ug = (ux * gx + uy * gy + uz * gz) * 2.0 / (s * s);
+    acc[0] += (2.0 * w * pg + 2.0 * (cx * gx + cy * gy + cz * gz)) / s - ug * w;
+    acc[1] += (-2.0 * pg * vx + 2.0 * vg * px + 2.0 * vp * gx + 2.0 * w * hx) / s - ug * vx;
+    acc[2] += (-2.0 * pg * vy + 2.0 * vg * py + 2.0 * vp * gy + 2.0 * w * hy) / s - ug * vy;
+    acc[3] += (-2.0 * pg * vz + 2.0 * vg * pz + 2.0 * vp * gz + 2.0 * w * hz) / s - ug * vz;
+    acc[4] += gx; acc[5] += gy; acc[6] += gz;
+    if (dxyz) {
+      const double ex = vy * gz - vz * gy, ey = vz * gx - vx * gz, ez = vx * gy - vy * gx;      // v x g
+      float* d = dxyz + (size_t)b * 3 * N;
+      d[n] = (float)((ww * gx + 2.0 * vg * vx - 2.0 * w * ex) / s);
+      d[N + n] = (float)((ww * gy + 2.0 * vg * vy - 2.0 * w * ey) / s);
+      d[2 * N + n] = (float)((ww * gz + 2.0 * vg * vz - 2.0 * w * ez) / s);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(PWCLO_FULL_MASK, v, o);
+    if (lane == 0) red[i][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    double v = 0.0;
+    for (int k = 0; k < kWarpThreads / 32; ++k) v += red[threadIdx.x][k];
+    if (threadIdx.x < 4) dq[b * 4 + threadIdx.x] = (float)v;
+    else dt[b * 3 + threadIdx.x - 4] = (float)v;
+  }
+}
+
 // Device-resident step counter and learning rate, so that a whole training step (forward, backward,
 // all-reduce, Adam) can be captured once in a CUDA graph and replayed: nothing step-dependent is baked into
 // kernel arguments.  state_i[0] = step count (incremented here), state_f = {lr (written by the host between
@@ -185,6 +264,23 @@ adam_step_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* 
 }
 
 }  // namespace pwclo
+
+PWCLO_API int pwclo_warp_fwd(const float* xyz, const float* q, const float* t, int B, int N, float* out, void* stream) {
+  if (!xyz || !q || !t || !out || B < 0 || N < 0) return PWCLO_EINVAL;
+  if (B == 0 || N == 0) return PWCLO_OK;
+  int gx = pwclo::ceil_div(N, pwclo::kWarpThreads);
+  if (gx > 64) gx = 64;
+  pwclo::warp_fwd_kernel<<<dim3(gx, B, 1), pwclo::kWarpThreads, 0, (cudaStream_t)stream>>>(xyz, q, t, N, out);
+  return pwclo::launch_status();
+}
+
+PWCLO_API int pwclo_warp_bwd(const float* xyz, const float* q, const float* grad_out, int B, int N, float* grad_xyz,
+                             float* grad_q, float* grad_t, void* stream) {
+  if (!xyz || !q || !grad_out || !grad_q || !grad_t || B < 0 || N < 0) return PWCLO_EINVAL;
+  if (B == 0) return PWCLO_OK;
+  pwclo::warp_bwd_kernel<<<B, pwclo::kWarpThreads, 0, (cudaStream_t)stream>>>(xyz, q, grad_out, N, grad_xyz, grad_q, grad_t);
+  return pwclo::launch_status();
+}
 
 PWCLO_API int pwclo_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
                                   int32_t* state_i, float* state_f, float beta1, float beta2, float eps, float weight_decay,

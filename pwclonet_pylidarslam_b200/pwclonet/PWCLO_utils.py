@@ -1,6 +1,8 @@
 """Quaternion helpers with the reference's names and term order (PW/PWCLO_utils.py:31-132).
 Quaternions are scalar-first; like the reference, the `scalar_last` arguments are accepted and
 ignored."""
+import os
+
 import torch
 
 
@@ -34,8 +36,53 @@ def mul_point_q(points, q, scalar_last: bool = False):
     return _hamilton(points.permute(0, 2, 1), q.reshape(B, 1, 4)).permute(0, 2, 1).contiguous()
 
 
+class FusedWarp(torch.autograd.Function):
+    """warp() as one sm_100a launch forward and one backward (pwclo_warp_fwd / pwclo_warp_bwd)"""
+
+    @staticmethod
+    def forward(ctx, xyz, q, t):
+        import ctypes
+        from .. import _lib
+        B, _, N = xyz.shape
+        xyz, q4, t3 = xyz.contiguous(), q.reshape(B, 4).contiguous(), t.reshape(B, 3).contiguous()
+        out = torch.empty_like(xyz)
+        p = lambda a: ctypes.c_void_p(a.data_ptr())
+        with torch.cuda.device(xyz.device):
+            _lib.check(_lib.lib().pwclo_warp_fwd(p(xyz), p(q4), p(t3), B, N, p(out), _lib.stream_ptr()), "warp_fwd")
+        ctx.save_for_backward(xyz, q4)
+        ctx.shapes = (q.shape, t.shape, ctx.needs_input_grad[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes
+        from .. import _lib
+        xyz, q4 = ctx.saved_tensors
+        qs, ts, need_x = ctx.shapes
+        B, _, N = xyz.shape
+        g = g.contiguous()
+        dq = torch.empty(B, 4, dtype=xyz.dtype, device=xyz.device)
+        dt = torch.empty(B, 3, dtype=xyz.dtype, device=xyz.device)
+        dx = torch.empty_like(xyz) if need_x else None
+        p = lambda a: ctypes.c_void_p(a.data_ptr()) if a is not None else None
+        with torch.cuda.device(xyz.device):
+            _lib.check(_lib.lib().pwclo_warp_bwd(p(xyz), p(q4), p(g), B, N, p(dx), p(dq), p(dt), _lib.stream_ptr()), "warp_bwd")
+        return dx, dq.reshape(qs), dt.reshape(ts)
+
+
+FUSED_WARP = os.environ.get("PWCLO_FUSED_WARP", "1") != "0"
+
+
 def warp(xyz, q, t, device=None, scalar_last: bool = False):
     """xyz [B,3,N], q [B,4,1], t [B,3,1] -> q (x) [0,xyz] (x) q^-1 + t   [B,3,N]"""
+    if (FUSED_WARP and xyz.is_cuda and xyz.dtype == torch.float32 and torch.is_grad_enabled()
+            and (q.requires_grad or t.requires_grad or xyz.requires_grad)):
+        return FusedWarp.apply(xyz, q, t)
+    return warp_composed(xyz, q, t)
+
+
+def warp_composed(xyz, q, t):
+    """the reference's expression tree, one torch op per term (used without autograd and as the parity reference)"""
     B, _, N = xyz.size()
     q_inv = inv_q(torch.squeeze(q, dim=2))
     xyz_ = torch.cat((torch.zeros([B, 1, N], device=xyz.device, dtype=xyz.dtype), xyz), dim=1)

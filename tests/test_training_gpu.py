@@ -232,3 +232,26 @@ def test_fused_bn_relu_train_matches_torch(cuda, shape):
     for name, a, r in zip(("y", "dx", "dgamma", "dbeta", "running_mean", "running_var"), got, want):
         err = float((a - r).abs().max())
         assert err <= 2e-5 * float(r.abs().max()) + 1e-7, (name, shape, err, float(r.abs().max()))
+
+
+@pytest.mark.parametrize("B,N", [(8, 2048), (3, 257), (5, 1)])
+def test_fused_warp_matches_composed(cuda, B, N):
+    """pwclo_warp_fwd/_bwd against the op-by-op torch expression of PW/PWCLO_utils.py:31-63 and its autograd:
+    forward to 1e-6, gradients wrt q, t and xyz to 1e-5 relative to the largest entry (non-unit quaternions too)"""
+    from pwclonet_pylidarslam_b200.pwclonet import PWCLO_utils as U
+    g = torch.Generator(device=cuda).manual_seed(B * 1000 + N)
+    xyz = (torch.randn(B, 3, N, device=cuda, generator=g) * 10).requires_grad_(True)
+    q = (torch.tensor([1.0, 0, 0, 0], device=cuda) + 0.4 * torch.randn(B, 4, device=cuda, generator=g)).reshape(B, 4, 1).requires_grad_(True)
+    t = torch.randn(B, 3, 1, device=cuda, generator=g).requires_grad_(True)
+    up = torch.randn(B, 3, N, device=cuda, generator=g)
+    out = U.FusedWarp.apply(xyz, q, t)
+    (out * up).sum().backward()
+    got = [out.detach(), xyz.grad.clone(), q.grad.clone(), t.grad.clone()]
+    xyz.grad = q.grad = t.grad = None
+    ref = U.warp_composed(xyz, q, t)
+    (ref * up).sum().backward()
+    want = [ref.detach(), xyz.grad, q.grad, t.grad]
+    for name, a, r, tol in zip(("out", "dxyz", "dq", "dt"), got, want, (2e-6, 1e-5, 1e-5, 1e-5)):
+        assert a.shape == r.shape, name
+        err = float((a - r).abs().max())
+        assert err <= tol * float(r.abs().max()) + 1e-7, (name, err, float(r.abs().max()))
