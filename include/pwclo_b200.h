@@ -243,6 +243,15 @@ int pwclo_bn_relu_train_fwd(const float *x, const float *gamma, const float *bet
 int pwclo_bn_relu_train_bwd(const float *x, const float *dy, const float *gamma, const float *beta,
                             const float *save_mean, const float *save_invstd, int B, int C, int HW,
                             float *dx, float *dgamma, float *dbeta, void *workspace, void *stream);
+/* 1x1 convolutions with very few channels (the first set-conv layers, 6 -> 8 -> 8 -> 16 on ~5e5 positions), for training:
+ * streaming forward / input gradient and a two-launch deterministic weight gradient dW[CO][CI] = sum dy * x.  Supported
+ * (CI, CO): forward / input gradient (6,8) (8,8) (8,16) (16,8) (3,8), weight gradient (6,8) (8,8) (8,16) (3,8);
+ * anything else returns PWCLO_EUNSUPPORTED and the caller keeps the library GEMM. */
+int pwclo_conv1x1_small(const float *x, const float *w, int transpose_w, int B, int CI, int CO, long long HW,
+                        float *y, void *stream);
+size_t pwclo_conv1x1_wgrad_workspace_bytes(int B, int CI, int CO, long long HW);
+int pwclo_conv1x1_wgrad(const float *x, const float *dy, int B, int CI, int CO, long long HW, float *dw,
+                        void *workspace, void *stream);
 
 /* ---- input pipeline ----------------------------------------------------------- */
 

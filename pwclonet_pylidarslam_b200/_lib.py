@@ -59,6 +59,8 @@ SIGNATURES = {
     "pwclo_bn_relu_train_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pwclo_warp_fwd": [_vp, _vp, _vp, _i, _i, _vp, _vp],
     "pwclo_warp_bwd": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
+    "pwclo_conv1x1_small": [_vp, _vp, _i, _i, _i, _i, ctypes.c_longlong, _vp, _vp],
+    "pwclo_conv1x1_wgrad": [_vp, _vp, _i, _i, _i, ctypes.c_longlong, _vp, _vp, _vp],
     "pwclo_pose_loss": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
 }
 
@@ -81,6 +83,8 @@ def lib():
             fn.restype = ctypes.c_int
         L.pwclo_knn_workspace_bytes.argtypes = [_i, _i, _i]
         L.pwclo_knn_workspace_bytes.restype = ctypes.c_size_t
+        L.pwclo_conv1x1_wgrad_workspace_bytes.argtypes = [_i, _i, _i, ctypes.c_longlong]
+        L.pwclo_conv1x1_wgrad_workspace_bytes.restype = ctypes.c_size_t
         L.pwclo_bn_relu_workspace_bytes.argtypes = [_i, _i, _i]
         L.pwclo_bn_relu_workspace_bytes.restype = ctypes.c_size_t
         L.pwclo_prepare_scans_workspace_bytes.argtypes = [ctypes.c_longlong, _i]

@@ -277,3 +277,162 @@ PWCLO_API int pwclo_bn_relu_train_bwd(const float* x, const float* dy, const flo
   }
   return launch_status();
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient of a 1x1 convolution with very few channels (the first set-conv layers: 6 -> 8 -> 8 on
+// [B, C, S*K] with S*K*B ~ 5e5 positions): dW[o][c] = sum over positions of dy[b,o,p] * x[b,c,p].  As a GEMM this is
+// M x N = 8 x 6 with K = 524 288: cuBLAS picks gemmSN_TN and needs 0.67 ms per call
+// (profiles/r1w_train_step_launches_fusedbn_summary.txt).  Here every thread keeps the CO x CI products in registers
+// over a strided slice of the positions (coalesced rows), a CTA reduces them, a second launch adds the CTA partials in
+// a fixed order (deterministic).
+namespace pwclo {
+
+constexpr int kWgThreads = 256;
+
+template <int CI, int CO>
+__global__ void __launch_bounds__(kWgThreads)
+conv1x1_wgrad_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, int B, long long HW,
+                             float* __restrict__ partial) {
+  __shared__ float red[kWgThreads / 32][CI * CO];
+  float acc[CO][CI];
+#pragma unroll
+  for (int o = 0; o < CO; ++o)
+#pragma unroll
+    for (int c = 0; c < CI; ++c) acc[o][c] = 0.f;
+  const long long total = (long long)B * HW;
+  for (long long p = (long long)blockIdx.x * kWgThreads + threadIdx.x; p < total; p += (long long)gridDim.x * kWgThreads) {
+    const long long b = p / HW, r = p - b * HW;
+    float xv[CI], gv[CO];
+#pragma unroll
+    for (int c = 0; c < CI; ++c) xv[c] = x[((size_t)b * CI + c) * HW + r];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) gv[o] = dy[((size_t)b * CO + o) * HW + r];
+#pragma unroll
+    for (int o = 0; o < CO; ++o)
+#pragma unroll
+      for (int c = 0; c < CI; ++c) acc[o][c] = fmaf(gv[o], xv[c], acc[o][c]);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 0; o < CO; ++o)
+#pragma unroll
+    for (int c = 0; c < CI; ++c) {
+      float v = acc[o][c];
+#pragma unroll
+      for (int s = 16; s; s >>= 1) v += __shfl_xor_sync(PWCLO_FULL_MASK, v, s);
+      if (lane == 0) red[warp][o * CI + c] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < CI * CO) {
+    float v = 0.f;
+    for (int w = 0; w < kWgThreads / 32; ++w) v += red[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * CI * CO + threadIdx.x] = v;
+  }
+}
+
+__global__ void conv1x1_wgrad_final_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = 0.0;
+  for (int p = 0; p < nparts; ++p) v += (double)partial[(size_t)p * n + i];
+  dw[i] = (float)v;
+}
+
+inline int wgrad_parts(int B, long long HW) {
+  long long want = ((long long)B * HW + 4 * kWgThreads - 1) / (4 * kWgThreads);
+  if (want > 4 * kNumSM) want = 4 * kNumSM;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+template <int CI, int CO>
+static int launch_wgrad(const float* x, const float* dy, int B, long long HW, float* dw, float* ws, cudaStream_t st) {
+  const int parts = wgrad_parts(B, HW);
+  conv1x1_wgrad_partial_kernel<CI, CO><<<parts, kWgThreads, 0, st>>>(x, dy, B, HW, ws);
+  conv1x1_wgrad_final_kernel<<<1, 128, 0, st>>>(ws, parts, CI * CO, dw);
+  return launch_status();
+}
+
+}  // namespace pwclo
+
+PWCLO_API size_t pwclo_conv1x1_wgrad_workspace_bytes(int B, int CI, int CO, long long HW) {
+  if (B <= 0 || CI <= 0 || CO <= 0 || HW <= 0) return 0;
+  return (size_t)pwclo::wgrad_parts(B, HW) * CI * CO * sizeof(float);
+}
+
+// supported (CI, CO): (6,8), (8,8), (8,16), (3,8) -- returns PWCLO_EUNSUPPORTED otherwise (the caller keeps torch's GEMM)
+PWCLO_API int pwclo_conv1x1_wgrad(const float* x, const float* dy, int B, int CI, int CO, long long HW, float* dw,
+                                  void* workspace, void* stream) {
+  using namespace pwclo;
+  if (!x || !dy || !dw || !workspace || B <= 0 || HW <= 0) return PWCLO_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = reinterpret_cast<float*>(workspace);
+  if (CI == 6 && CO == 8) return launch_wgrad<6, 8>(x, dy, B, HW, dw, ws, st);
+  if (CI == 8 && CO == 8) return launch_wgrad<8, 8>(x, dy, B, HW, dw, ws, st);
+  if (CI == 8 && CO == 16) return launch_wgrad<8, 16>(x, dy, B, HW, dw, ws, st);
+  if (CI == 3 && CO == 8) return launch_wgrad<3, 8>(x, dy, B, HW, dw, ws, st);
+  return PWCLO_EUNSUPPORTED;
+}
+
+// y[b,o,p] = sum_c W[o][c] * x[b,c,p] for the same skinny shapes (forward), or with `transpose_w` the input gradient
+// dx[b,c,p] = sum_o W[o][c] * dy[b,o,p] (CI / CO then name the channels of the tensor read / written).  One pass,
+// float4 per channel row: the op is pure streaming ((CI + CO) * 4 B per position) where the GEMM libraries spend
+// 0.2 ms per call on a 64x64 tensor-op tile that is 90 % padding.
+namespace pwclo {
+
+template <int CI, int CO>
+__global__ void __launch_bounds__(256)
+conv1x1_small_kernel(const float* __restrict__ x, const float* __restrict__ w, int transpose_w, int B, long long HW4,
+                     float* __restrict__ y) {
+  __shared__ float sw[CO * CI];
+  for (int i = threadIdx.x; i < CO * CI; i += 256) {
+    const int o = i / CI, c = i - o * CI;
+    sw[i] = transpose_w ? w[c * CO + o] : w[o * CI + c];      // transposed: w is stored [CI_out_of_conv = CI here][CO]
+  }
+  __syncthreads();
+  const long long total = (long long)B * HW4;
+  for (long long u = (long long)blockIdx.x * 256 + threadIdx.x; u < total; u += (long long)gridDim.x * 256) {
+    const long long b = u / HW4, r = u - b * HW4;
+    float4 xv[CI];
+#pragma unroll
+    for (int c = 0; c < CI; ++c) xv[c] = reinterpret_cast<const float4*>(x + ((size_t)b * CI + c) * HW4 * 4)[r];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < CI; ++c) {
+        const float ww = sw[o * CI + c];
+        a.x = fmaf(ww, xv[c].x, a.x); a.y = fmaf(ww, xv[c].y, a.y); a.z = fmaf(ww, xv[c].z, a.z); a.w = fmaf(ww, xv[c].w, a.w);
+      }
+      reinterpret_cast<float4*>(y + ((size_t)b * CO + o) * HW4 * 4)[r] = a;
+    }
+  }
+}
+
+template <int CI, int CO>
+static int launch_small(const float* x, const float* w, int tr, int B, long long HW, float* y, cudaStream_t st) {
+  const long long units = (long long)B * (HW / 4);
+  long long blocks = (units + 255) / 256;
+  if (blocks > 8 * kNumSM) blocks = 8 * kNumSM;
+  conv1x1_small_kernel<CI, CO><<<(int)blocks, 256, 0, st>>>(x, w, tr, B, HW / 4, y);
+  return launch_status();
+}
+
+}  // namespace pwclo
+
+// x [B,CI,HW] -> y [B,CO,HW]; w is the conv weight: [CO][CI] (transpose_w = 0) or, for the input gradient, the weight
+// [CI][CO] of the forward conv read transposed (transpose_w = 1).  HW % 4 == 0, 16-byte aligned tensors.
+PWCLO_API int pwclo_conv1x1_small(const float* x, const float* w, int transpose_w, int B, int CI, int CO, long long HW, float* y,
+                                  void* stream) {
+  using namespace pwclo;
+  if (!x || !w || !y || B <= 0 || HW <= 0) return PWCLO_EINVAL;
+  if (HW % 4 != 0 || (((uintptr_t)x | (uintptr_t)y) & 15) != 0) return PWCLO_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tr = transpose_w ? 1 : 0;
+  if (CI == 6 && CO == 8) return launch_small<6, 8>(x, w, tr, B, HW, y, st);
+  if (CI == 8 && CO == 8) return launch_small<8, 8>(x, w, tr, B, HW, y, st);
+  if (CI == 8 && CO == 16) return launch_small<8, 16>(x, w, tr, B, HW, y, st);
+  if (CI == 16 && CO == 8) return launch_small<16, 8>(x, w, tr, B, HW, y, st);
+  if (CI == 3 && CO == 8) return launch_small<3, 8>(x, w, tr, B, HW, y, st);
+  return PWCLO_EUNSUPPORTED;
+}

@@ -13,6 +13,8 @@
 //     reference, and exact ties are resolved exactly like the reference's tree: the candidate with
 //     the smallest (bit-reversed (k mod T), k) wins, T = the reference's block size for this n
 //     (EXT/include/cuda_utils.h:13-19).  See DESIGN.md "FPS tie order".
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -358,6 +360,128 @@ static int launch_fps_slab(const float* xyz, int B, int n, int m, int logT, int 
   return launch_status();
 }
 
+// -------------------------------------------------------------------------------------------------
+// Cluster variant for FEW clouds (B * 8 <= SM count: training at 8 pairs per GPU, single-pair inference).  One CTA
+// per cloud leaves most of the machine idle and makes every one of the m-1 dependent rounds pay for all n points
+// on one SM (n = 16384: coordinates do not even fit the register file, 1.7 us per round).  Here a thread-block
+// cluster of 8 CTAs owns a cloud: point k lives in the registers of global thread k mod 2048 (so a thread's points
+// share k mod T and ascend in k, which keeps the reference's tie order exactly as in the kernels above), every CTA
+// finds its local arg-max, writes (value, key, xyz of that point) into a slot of ALL eight CTAs through distributed
+// shared memory, one cluster barrier, and every CTA picks the winner from its own eight slots.  Per round: n/8 point
+// updates per SM, one __syncthreads, one cluster barrier; slots are double-buffered.  Same result, bit for bit.
+// -------------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int kFpsCluster = 8;
+constexpr int kFpsClThreads = 256;
+
+struct FpsCand { unsigned val, key; float x, y, z; };
+
+template <int P>
+__global__ void __launch_bounds__(kFpsClThreads, 1)
+fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origin_skip, int32_t* __restrict__ idx) {
+  constexpr int THREADS = kFpsClThreads, CL = kFpsCluster, TT = THREADS * CL, NW = THREADS / 32;
+  __shared__ float sx[P * THREADS], sy[P * THREADS], sz[P * THREADS];     // this CTA's points, slot = j*THREADS + tid
+  __shared__ unsigned red_val[2][NW], red_key[2][NW];
+  __shared__ FpsCand cand[2][CL];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gt = rank * THREADS + tid;                 // global thread of the cloud: owns points gt, gt + TT, ...
+  xyz += (size_t)b * n * 3;
+  idx += (size_t)b * m;
+
+  float px[P], py[P], pz[P], mind[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int k = gt + j * TT;
+    float x = 0.f, y = 0.f, z = 0.f;
+    bool valid = k < n;
+    if (valid) {
+      x = xyz[k * 3 + 0]; y = xyz[k * 3 + 1]; z = xyz[k * 3 + 2];
+      if (origin_skip) {
+        const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
+        valid = !((double)mag <= 1e-3);
+      }
+    }
+    px[j] = x; py[j] = y; pz[j] = z;
+    sx[j * THREADS + tid] = x; sy[j * THREADS + tid] = y; sz[j * THREADS + tid] = z;
+    mind[j] = valid ? 1e10f : -1.0f;
+  }
+  if (rank == 0 && tid == 0) idx[0] = 0;
+  float x1 = xyz[0], y1 = xyz[1], z1 = xyz[2];         // the first sample is point 0
+  __syncthreads();
+
+  for (int r = 1; r < m; ++r) {
+    float best = -1.0f;
+    int bestk = 0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const float d = dist2_ref_fma(px[j] - x1, py[j] - y1, pz[j] - z1);
+      const float d2 = fminf(d, mind[j]);
+      mind[j] = d2;
+      if (d2 > best) { best = d2; bestk = gt + j * TT; }
+    }
+    const unsigned vb = best < 0.f ? 0u : __float_as_uint(best) + 1u;
+    const unsigned key = fps_key((unsigned)bestk, logT);
+    const unsigned wv = __reduce_max_sync(PWCLO_FULL_MASK, vb);
+    const unsigned wk = __reduce_min_sync(PWCLO_FULL_MASK, vb == wv ? key : 0xffffffffu);
+    const int buf = r & 1;
+    if (lane == 0) { red_val[buf][warp] = wv; red_key[buf][warp] = wk; }
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned v2 = lane < NW ? red_val[buf][lane] : 0u;
+      const unsigned k2 = lane < NW ? red_key[buf][lane] : 0xffffffffu;
+      const unsigned bv = __reduce_max_sync(PWCLO_FULL_MASK, v2);
+      const unsigned bk = __reduce_min_sync(PWCLO_FULL_MASK, v2 == bv ? k2 : 0xffffffffu);
+      if (lane < CL) {
+        FpsCand c;
+        c.val = bv; c.key = bk; c.x = 0.f; c.y = 0.f; c.z = 0.f;
+        if (bv != 0u) {
+          const int k = (int)fps_key_to_index(bk, logT);           // a point of this CTA
+          const int slot = (k / TT) * THREADS + (k % TT - rank * THREADS);
+          c.x = sx[slot]; c.y = sy[slot]; c.z = sz[slot];
+        }
+        *cluster.map_shared_rank(&cand[buf][rank], lane) = c;      // my candidate into CTA `lane`'s slot table
+      }
+    }
+    cluster.sync();
+    unsigned bv = 0u, bk = 0xffffffffu;
+    int who = 0;
+#pragma unroll
+    for (int c = 0; c < CL; ++c) {
+      const unsigned v = cand[buf][c].val, k = cand[buf][c].key;
+      if (v > bv || (v == bv && k < bk)) { bv = v; bk = k; who = c; }
+    }
+    int old = 0;
+    if (bv != 0u) {
+      old = (int)fps_key_to_index(bk, logT);
+      x1 = cand[buf][who].x; y1 = cand[buf][who].y; z1 = cand[buf][who].z;
+    } else {
+      x1 = xyz[0]; y1 = xyz[1]; z1 = xyz[2];                        // no valid candidate: the reference re-selects index 0
+    }
+    if (rank == 0 && tid == 0) idx[r] = old;
+  }
+  cluster.sync();        // nobody exits while a neighbour may still write into its slot table
+}
+
+template <int P>
+static int launch_fps_cluster(const float* xyz, int B, int n, int m, int logT, int origin_skip, int32_t* idx, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kFpsCluster, B, 1);
+  cfg.blockDim = dim3(kFpsClThreads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kFpsCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, fps_cluster_kernel<P>, xyz, n, m, logT, origin_skip, idx);
+  return e == cudaSuccess ? launch_status() : (int)e;
+}
+
 template <int P, int THREADS, int MODE>
 static int launch_fps(const float* xyz, int B, int n, int m, int logT, int origin_skip, float* scratch, int32_t* idx,
                       cudaStream_t st) {
@@ -386,6 +510,21 @@ PWCLO_API int pwclo_furthest_point_sampling(const float* xyz, int B, int N, int 
   int T = 1, logT = 0;
   while (T * 2 <= N && T * 2 <= cap) { T *= 2; ++logT; }
   const int skip = (flags & PWCLO_FPS_ORIGIN_SKIP) ? 1 : 0;
+  // few clouds: a cluster of 8 CTAs per cloud (see fps_cluster_kernel); PWCLO_FPS_CLUSTER=0 disables
+  {
+    const char* ce = getenv("PWCLO_FPS_CLUSTER");
+    const bool allow = !(ce && ce[0] == '0');
+    // Measured on the B200 (tools/bench_fps_cluster.py): a round costs 0.8-1.1 us whatever n is -- the cluster barrier
+    // and the DSMEM exchange, not the point updates -- so the cluster wins only where one CTA per cloud is slow:
+    // n > 8192 (16 clouds x 16384 -> 2048: 2.23 ms against 3.57 ms); at n <= 8192 the register-resident slab kernel
+    // needs 0.43 us per round and stays the choice (PWCLO_FPS_CLUSTER=2 forces the cluster there, for tests).
+    const bool force = ce && ce[0] == '2';
+    if (allow && m >= 64 && N >= 2048 && N <= 16384 && (N > 8192 || force) && B * kFpsCluster <= kNumSM) {
+      if (N <= 4096) return launch_fps_cluster<2>(xyz, B, N, m, logT, skip, idx, st);
+      if (N <= 8192) return launch_fps_cluster<4>(xyz, B, N, m, logT, skip, idx, st);
+      return launch_fps_cluster<8>(xyz, B, N, m, logT, skip, idx, st);
+    }
+  }
   // THREADS must be a multiple of T so that a thread's points share (k mod T): 512 or 1024 (cap 1024)
   // slab-skipping kernel: worth its two in-kernel sorts once there are enough rounds and points
   const char* slab_min = getenv("PWCLO_FPS_SLAB_MIN_N");

@@ -66,6 +66,21 @@ def test_fps_orphan_variant(cuda, B, N, m, kind):
     np.testing.assert_array_equal(got, want)
 
 
+@pytest.mark.parametrize("B,N,m,kind,flags", [(3, 16384, 600, "lidar", 1), (2, 12000, 300, "dups", 1), (2, 4096, 500, "grid", 1),
+                                              (4, 4096, 256, "origin", 1), (2, 3000, 200, "dups", 2), (1, 16384, 300, "rand", 2)])
+def test_fps_cluster_kernel_bit_exact(cuda, monkeypatch, B, N, m, kind, flags):
+    """the 8-CTA cluster kernel (default for n > 8192 with few clouds; forced here for the smaller sizes) against the
+    C oracle: exact ties (duplicates, lattice), origin-ball points and both tie orders included"""
+    monkeypatch.setenv("PWCLO_FPS_CLUSTER", "2")
+    x = _fps_input(kind, B, N, seed=N + m + flags)
+    want = cpu_ops.fps(x, m, origin_skip=(flags == 1), thread_cap=512 if flags == 1 else 1024)
+    got = _ext.furthest_point_sampling(_dev(x, cuda), m, flags=flags).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    monkeypatch.setenv("PWCLO_FPS_CLUSTER", "0")
+    one = _ext.furthest_point_sampling(_dev(x, cuda), m, flags=flags).cpu().numpy()
+    np.testing.assert_array_equal(one, want)
+
+
 def test_fps_nested_prefix_property(cuda):
     """FPS of an FPS prefix is the prefix -- size-independent property at full size."""
     x = np.stack([synthetic.make_pair(synthetic.SEED_BASE + 7, 8192)["pc2"]])

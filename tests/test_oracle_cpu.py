@@ -133,7 +133,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/pwclo_b200.h but not exported"
     assert declared - {"pwclo_version", "pwclo_error_string", "pwclo_knn_workspace_bytes", "pwclo_prepare_scans_workspace_bytes",
-                       "pwclo_bn_relu_workspace_bytes"} == set(_lib.SIGNATURES), "ctypes table out of sync"
+                       "pwclo_bn_relu_workspace_bytes", "pwclo_conv1x1_wgrad_workspace_bytes"} == set(_lib.SIGNATURES), "ctypes table out of sync"
     assert b"sm_100a" in _lib.lib().pwclo_version()
 
 

@@ -255,3 +255,29 @@ def test_fused_warp_matches_composed(cuda, B, N):
         assert a.shape == r.shape, name
         err = float((a - r).abs().max())
         assert err <= tol * float(r.abs().max()) + 1e-7, (name, err, float(r.abs().max()))
+
+
+@pytest.mark.parametrize("B,CI,CO,S,K,need_dx", [(8, 6, 8, 2048, 32, False), (4, 8, 8, 1024, 32, True), (2, 8, 16, 2048, 16, True),
+                                                 (3, 3, 8, 4096, 8, True)])
+def test_skinny_conv1x1_matches_torch(cuda, B, CI, CO, S, K, need_dx):
+    """pwclo_conv1x1_small / pwclo_conv1x1_wgrad against F.conv2d and its autograd (fp32, TF32 off): 1e-5 relative to
+    the largest entry on y, dW (a 5e5-term sum) and dx"""
+    from pwclonet_pylidarslam_b200.pytorch_utils import SkinnyConv1x1
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device=cuda).manual_seed(CI * 100 + CO)
+    x = torch.randn(B, CI, S, K, device=cuda, generator=g).requires_grad_(need_dx)
+    w = (torch.randn(CO, CI, 1, 1, device=cuda, generator=g) * 0.4).requires_grad_(True)
+    up = torch.randn(B, CO, S, K, device=cuda, generator=g)
+    y = SkinnyConv1x1.apply(x, w)
+    (y * up).sum().backward()
+    got = [y.detach(), w.grad.clone()] + ([x.grad.clone()] if need_dx else [])
+    w.grad = None
+    if need_dx:
+        x.grad = None
+    yr = torch.nn.functional.conv2d(x, w)
+    (yr * up).sum().backward()
+    want = [yr.detach(), w.grad] + ([x.grad] if need_dx else [])
+    for name, a, r in zip(("y", "dw", "dx"), got, want):
+        err = float((a - r).abs().max())
+        assert err <= 1e-5 * float(r.abs().max()) + 1e-7, (name, err, float(r.abs().max()))
