@@ -438,6 +438,10 @@ class PWCLONetTrainer:
         `batch` (its first four entries are copied into static buffers).  The `warmup` eager steps it runs first
         ARE training steps.  The graph stays valid across steps and learning-rate changes (step counter and lr
         live in device memory); it is dropped when the BN momentum changes (a captured scalar) or on train(False)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            raise NotImplementedError(
+                "capture() is single-process for now: with the NCCL all-reduce inside the captured step a 2-GPU run hung "
+                "(round-1 measurement); use train_step() for data-parallel training")
         self.prediction_module_.train()
         self.loss_module_.train()
         self._static_batch = [b.to(self.device).clone() if torch.is_tensor(b) else b for b in batch[:4]]
