@@ -153,6 +153,20 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def host_info():
+    """what the CPU numbers were measured on (core count, torch threads, CPU model)"""
+    model = None
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except Exception:
+        pass
+    return {"cpu_count": os.cpu_count() or 1, "torch_threads": torch.get_num_threads(), "cpu_model": model}
+
+
 def cpu_reference(weights, steps, warmup, pairs_per_step=1):
     """The reference forward on the host cores: oracle port with the reference's own (materialising,
     torch.topk) kNN formulation and all host threads.  Returns (pairs/s, ms/step, description)."""
@@ -184,7 +198,7 @@ def run_reference(args, rank):
             "config": {"workload": "PWCLO-Net inference forward, 8192-point synthetic KITTI-64-beam frame pairs, "
                                    "reference CPU path (oracle port of the reference forward; the reference's CUDA "
                                    "extension has no CPU path), 1 pair per step"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "host": host_info()},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -501,7 +515,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, ms, sample = cpu_reference(weights, 5, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": sample, "ms_per_pair": ms}
+                                    "sample": sample, "ms_per_pair": ms, "host": host_info()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -92,3 +92,23 @@ def test_kitti360_crop_equals_reference_expression():
     pts, sel, M = S.prepare_scan(raw, scan_input.IDENTITY_TR, 0, 3, 16384, crop=crop)
     assert M == S.reference_mask_kitti360(raw[:, :3]).sum() and pts.shape == (16384, 3)
     np.testing.assert_array_equal(pts, raw[sel, :3])
+
+
+def test_pack_scans_and_pairs_host_side():
+    """host packing: one buffer + int64 offsets; a frame pair is cut to the shorter scan first (reference :378-384)"""
+    from pwclonet_pylidarslam_b200 import scan_input
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((1000, 4)).astype(np.float32)
+    b = rng.standard_normal((700, 4)).astype(np.float32)
+    c = rng.standard_normal((5, 4)).astype(np.float32)
+    buf, off, mx = scan_input.pack_scans([a, b, c], pin=False)
+    assert buf.shape == (1705, 4) and off.tolist() == [0, 1000, 1700, 1705] and mx == 1000
+    np.testing.assert_array_equal(buf[1000:1700].numpy(), b)
+    buf, off, mx = scan_input.pack_pairs([a, c], [b, a], pin=False)
+    assert off.tolist() == [0, 700, 1400, 1405, 1410] and mx == 700
+    np.testing.assert_array_equal(buf[:700].numpy(), a[:700])
+    np.testing.assert_array_equal(buf[1405:1410].numpy(), a[:5])
+    # crop helpers: KITTI-360 thresholds are float32-rounded, the KITTI odometry ones are the reference literals
+    g = scan_input.kitti360_crop(30.0)
+    assert g[:2] == (2, -1) and g[2] == float(np.float32(-1.43)) and g[3:5] == (0, 1) and g[5] == 30.0
+    assert scan_input.KITTI_ODOMETRY_CROP == (1, 1, 1.1, 0, 2, 30.0)
