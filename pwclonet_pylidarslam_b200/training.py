@@ -21,6 +21,7 @@ There is no CPU path: the loss and the optimiser raise on CPU tensors.
 """
 import ctypes
 import math
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -438,10 +439,13 @@ class PWCLONetTrainer:
         `batch` (its first four entries are copied into static buffers).  The `warmup` eager steps it runs first
         ARE training steps.  The graph stays valid across steps and learning-rate changes (step counter and lr
         live in device memory); it is dropped when the BN momentum changes (a captured scalar) or on train(False)."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if multi and os.environ.get("PWCLO_GRAPH_DDP") != "1":
             raise NotImplementedError(
                 "capture() is single-process for now: with the NCCL all-reduce inside the captured step a 2-GPU run hung "
-                "(round-1 measurement); use train_step() for data-parallel training")
+                "(round-1 measurement); use train_step() for data-parallel training.  PWCLO_GRAPH_DDP=1 tries the "
+                "untested variant that captures with capture_error_mode='thread_local' (the NCCL watchdog thread's "
+                "event queries are the first suspect)")
         self.prediction_module_.train()
         self.loss_module_.train()
         self._static_batch = [b.to(self.device).clone() if torch.is_tensor(b) else b for b in batch[:4]]
@@ -454,7 +458,7 @@ class PWCLONetTrainer:
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        with torch.cuda.graph(self._graph, **({"capture_error_mode": "thread_local"} if multi else {})):
             self._static_out = self._step_body(self._static_batch)
         self.train_iter += 1                          # capture executes nothing, but the step below replays it once
         self._graph.replay()

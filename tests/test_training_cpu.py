@@ -149,3 +149,22 @@ def test_two_rank_gradient_allreduce_equals_full_batch(tmp_path):
     x = torch.tensor(np.concatenate([r0[1 + n:].reshape(6, 5), r1[1 + n:].reshape(6, 5)]), dtype=torch.float32)
     net(x).square().mean().backward()                                  # the full batch on one process
     np.testing.assert_allclose(r0[1:1 + n], arena.grad.numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_no_cpu_path_anywhere_in_the_new_rows():
+    """trainer, odometry adapter, streaming pipeline, optimiser and pose post-processing refuse CPU devices / tensors
+    instead of falling back"""
+    from pwclonet_pylidarslam_b200 import odometry as O
+    from pwclonet_pylidarslam_b200 import sharding
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        T.PWCLONetTrainer(T.PWCLONetTrainerConfig(device="cpu"))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        O.PWCLONetOdometry({"device": "cpu"})
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        sharding.PosePipeline(nn.Linear(2, 2), 1, 8)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        T.FlatAdam(T.FlatArena([_tiny()]))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        O.pose_params_to_matrices(torch.zeros(2, 4, 7))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        O.convert_to_absolute(torch.zeros(2, 4, 4, dtype=torch.float64))
