@@ -147,3 +147,29 @@ class PWCLONetOdometry:
 
     def get_elapsed(self):
         return sum(self.elapsed)
+
+
+def save_poses(poses, file_path, frames=None):
+    """KITTI-style pose text file as the reference writes it (KITTI360_IO.save_poses,
+    slam/common/kitti360_utils.py:267-304, used by train.py:935-952): one line per frame,
+    `frame r00 r01 r02 tx r10 ... tz`, blank-separated, floats in their shortest round-trip form (what
+    pandas.DataFrame.to_csv emits).  poses: [F,4,4] / [F,3,4] / [F,12] array or tensor (a CUDA tensor is read back
+    once), or a dict frame -> 4x4; frames default to 0..F-1."""
+    if poses is None:
+        raise RuntimeError("[save_poses]: poses is None")
+    if isinstance(poses, dict):
+        keys = sorted(poses.keys())
+        frames = [int(k) for k in keys]
+        arr = np.stack([np.asarray(poses[k], dtype=np.float64)[:3, :] for k in keys]).reshape(len(keys), 12)
+    else:
+        if torch.is_tensor(poses):
+            poses = poses.detach().cpu().numpy()
+        arr = np.asarray(poses, dtype=np.float64)
+        if arr.ndim == 3 and arr.shape[1:] in ((4, 4), (3, 4)):
+            arr = arr[:, :3, :].reshape(arr.shape[0], 12)
+        elif not (arr.ndim == 2 and arr.shape[1] == 12):
+            raise RuntimeError("[save_poses]: poses should be an array of size (-1, 4, 4), (-1, 3, 4) or (-1, 12)")
+        frames = list(range(arr.shape[0])) if frames is None else [int(f) for f in frames]
+    with open(file_path, "w") as f:
+        for fr, row in zip(frames, arr):
+            f.write(" ".join([str(fr)] + [repr(float(v)) for v in row]) + "\n")

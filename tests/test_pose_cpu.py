@@ -41,3 +41,34 @@ def test_convert_to_absolute_equals_reference():
     got = P.convert_to_absolute([rel[i] for i in range(50)])
     for i in range(50):
         np.testing.assert_array_equal(got[i], want[i])
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not mounted")
+def test_save_poses_equals_reference_text(tmp_path):
+    """the KITTI pose text file, byte for byte, against the reference's KITTI360_IO.save_poses (pandas to_csv)"""
+    import pandas as pd
+    from pwclonet_pylidarslam_b200 import odometry as O
+    src = open(REF).read()
+    start = src.index("class KITTI360_IO")
+    end = src.index("class KITTI360_TRANSFORMATIONS")
+    body = src[start:end]
+    # only save_poses is needed: cut the class down to that method
+    a = body.index("    def save_poses")
+    b = body.index("    def loadWindowNpy")
+    ns = {"np": np, "pd": pd}
+    exec(compile("class KITTI360_IO:\n" + body[a:b], REF, "exec"), ns)
+    ref = ns["KITTI360_IO"].save_poses
+    rng = np.random.default_rng(2)
+    rel = [P.relative_pose(np.concatenate([rng.normal(0, 1, 3), [1, 0, 0, 0] + 0.05 * rng.standard_normal(4)]).astype(np.float32))
+           for _ in range(40)]
+    absolute = P.convert_to_absolute(rel)
+    absolute[0] = np.eye(4)                                   # exact 1.0 / 0.0 entries
+    absolute[1][0, 3] = 1e-17
+    absolute[2][1, 3] = 123456789.125
+    d = {3 * i + 7: absolute[i] for i in range(40)}           # dict form with sparse frame ids
+    ref(d, str(tmp_path / "ref_dict.txt"))
+    O.save_poses(d, str(tmp_path / "our_dict.txt"))
+    assert open(tmp_path / "ref_dict.txt").read() == open(tmp_path / "our_dict.txt").read()
+    ref(absolute, str(tmp_path / "ref_arr.txt"))
+    O.save_poses(absolute, str(tmp_path / "our_arr.txt"))
+    assert open(tmp_path / "ref_arr.txt").read() == open(tmp_path / "our_arr.txt").read()
