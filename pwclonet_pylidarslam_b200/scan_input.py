@@ -79,3 +79,29 @@ def prepare_scans(raw, offsets, Tr, npoints, seed, post=None, max_points=None, r
                                               int(crop[1]), float(crop[2]), int(crop[3]), int(crop[4]), float(crop[5]),
                                               p(out), p(idx), p(surv), p(ws), ws.numel(), _lib.stream_ptr()), "prepare_scans")
     return (out, idx, surv) if return_index else out
+
+
+def load_kitti_bin(path):
+    """a KITTI / KITTI-360 velodyne scan file -> float32 [n,4] (x, y, z, reflectance), exactly
+    `np.fromfile(path, dtype=np.float32).reshape(-1, 4)` (kitti_odometry_dataset.py:375-376)"""
+    a = np.fromfile(path, dtype=np.float32)
+    if a.size % 4 != 0:
+        raise RuntimeError(f"{path}: {a.size} floats is not a whole number of (x, y, z, reflectance) records")
+    return a.reshape(-1, 4)
+
+
+def prepare_pairs_from_files(files_current, files_previous, Tr, npoints, seed, device="cuda:0", crop=KITTI_ODOMETRY_CROP, post=None):
+    """frame pairs from scan files to network inputs: read, cut each pair to its shorter scan, pack into one pinned
+    buffer, one H2D copy, `prepare_scans`.  Returns (xyz_f1 [P,npoints,3], xyz_f2 [P,npoints,3]) on `device` with
+    frame 1 = current and frame 2 = previous scan, the order the KITTI dataset feeds PWCLO-Net
+    (kitti_odometry_dataset.py:330-343, 462-463).  Tr: [3,4] / [4,4] array (identity rows for KITTI-360)."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("prepare_pairs_from_files needs a CUDA device (there is no CPU path)")
+    cur = [load_kitti_bin(p) for p in files_current]
+    prev = [load_kitti_bin(p) for p in files_previous]
+    buf, off, _ = pack_pairs(cur, prev)
+    Tr = np.ascontiguousarray(np.asarray(Tr, np.float64)[:3, :4])
+    clouds = prepare_scans(buf.to(dev, non_blocking=True), off.to(dev), torch.from_numpy(Tr).to(dev), npoints, seed,
+                           post=post, crop=crop)
+    return clouds[0::2].contiguous(), clouds[1::2].contiguous()

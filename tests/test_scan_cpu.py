@@ -112,3 +112,19 @@ def test_pack_scans_and_pairs_host_side():
     g = scan_input.kitti360_crop(30.0)
     assert g[:2] == (2, -1) and g[2] == float(np.float32(-1.43)) and g[3:5] == (0, 1) and g[5] == 30.0
     assert scan_input.KITTI_ODOMETRY_CROP == (1, 1, 1.1, 0, 2, 30.0)
+
+
+def test_kitti_bin_reader(tmp_path):
+    from pwclonet_pylidarslam_b200 import scan_input
+    import pytest
+    raw = syn.make_raw_scan(9)[:1234]
+    p = tmp_path / "000000.bin"
+    raw.tofile(p)
+    got = scan_input.load_kitti_bin(str(p))
+    assert got.dtype == np.float32 and got.shape == (1234, 4)
+    np.testing.assert_array_equal(got, raw)
+    (tmp_path / "bad.bin").write_bytes(b"\x00" * 20)
+    with pytest.raises(RuntimeError, match="whole number"):
+        scan_input.load_kitti_bin(str(tmp_path / "bad.bin"))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        scan_input.prepare_pairs_from_files([str(p)], [str(p)], syn.KITTI_TR, 64, 0, device="cpu")
