@@ -6,6 +6,16 @@ import os
 import torch
 
 
+def switch_quat(q, scalar_last: bool = False):
+    """numpy quaternion(s) [4] or [B,4]: scalar-first -> scalar-last (scalar_last=True) or back (PW/PWCLO_utils.py:5-28;
+    not used by the network, kept for the module's surface)"""
+    import numpy as np
+    q = np.asarray(q)
+    if q.ndim not in (1, 2):
+        raise RuntimeError(f"[switch_quat] Unrecognized shape of quaternions: {q.shape}")
+    return np.roll(q, -1 if scalar_last else 1, axis=-1)
+
+
 def inv_q(q, device=None, scalar_last: bool = False):
     """q^-1 = conj(q) / (|q|^2 + 1e-10); q [B,4]"""
     q_2 = torch.sum(q * q, dim=-1, keepdim=True) + 1e-10

@@ -192,6 +192,14 @@ class SharedMLP(nn.Sequential):
             self.add_module(name + f"layer{i}", Conv2d(args[i], args[i + 1], bn=bn, activation=activation, init=init))
 
 
+def set_bn_momentum_default(bn_momentum):
+    """P2/pytorch_utils.py:310-316: the function BNMomentumScheduler applies to every module"""
+    def fn(m):
+        if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)):
+            m.momentum = bn_momentum
+    return fn
+
+
 class BNMomentumScheduler(object):
     """P2/pytorch_utils.py:319-347."""
 

@@ -153,3 +153,23 @@ def test_ext_refuses_cpu_tensors():
         _ext.furthest_point_sampling(torch.zeros(1, 8, 3), 2)
     with pytest.raises(RuntimeError):
         _ext.knn(torch.zeros(1, 8, 3), torch.zeros(1, 2, 3), 2)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted")
+def test_small_helpers_equal_reference():
+    """switch_quat and set_bn_momentum_default behave as the reference's (module surface parity)"""
+    ref_shim.load_reference()
+    mods = ref_shim.reference_modules()
+    from pwclonet_pylidarslam_b200 import pytorch_utils as ours_pt
+    from pwclonet_pylidarslam_b200.pwclonet import PWCLO_utils as ours_u
+    rng = np.random.default_rng(0)
+    for shape in ((4,), (5, 4)):
+        q = rng.standard_normal(shape).astype(np.float32)
+        for last in (True, False):
+            np.testing.assert_array_equal(ours_u.switch_quat(q, last), mods["PWCLO_utils"].switch_quat(q, last))
+    with pytest.raises(RuntimeError):
+        ours_u.switch_quat(np.zeros((2, 3, 4)))
+    a, b = torch.nn.Sequential(torch.nn.BatchNorm2d(3), torch.nn.Conv2d(3, 3, 1)), torch.nn.Sequential(torch.nn.BatchNorm2d(3))
+    a.apply(ours_pt.set_bn_momentum_default(0.37))
+    b.apply(mods["pytorch_utils"].set_bn_momentum_default(0.37))
+    assert a[0].momentum == b[0].momentum == 0.37
