@@ -49,6 +49,18 @@ const char *pwclo_error_string(int code);
  * buffer: the running minimum distances live in registers. */
 int pwclo_furthest_point_sampling(const float *xyz, int B, int N, int m, unsigned flags,
                                   int32_t *idx, void *stream);
+/* Same sampling with the prefix property made usable (PW/pwclo_net.py:130-138,164 chains FPS on FPS
+ * output: P2/pointnet2_modules.py:200-206 at every level): FPS of a cloud that is itself the
+ * FPS-ordered output of a tie-free run returns 0..m-1.
+ *   tie_out (optional, int32[B]): set to 1 for the clouds whose run saw two candidates tie for an
+ *     arg-max (or ran out of valid candidates), else 0.  Conservative: 1 may be a false alarm.
+ *   tie_in  (optional, int32[B]): the tie_out of the run that PRODUCED xyz (xyz[b] = the points it
+ *     selected, in selection order, same flags).  Clouds with tie_in[b] == 0 get idx = 0..m-1
+ *     without running the m-1 dependent rounds; the others are sampled for real.  Bit-identical to
+ *     pwclo_furthest_point_sampling either way.  Requires m <= N. */
+int pwclo_furthest_point_sampling_prefix(const float *xyz, int B, int N, int m, unsigned flags,
+                                         int32_t *idx, const int32_t *tie_in, int32_t *tie_out,
+                                         void *stream);
 
 /* gather_points(points[B,C,N], idx[B,M]) -> out[B,C,M]           EXT/src/sampling.cpp:15-39 */
 int pwclo_gather_points(const float *points, const int32_t *idx, int B, int C, int N, int M,

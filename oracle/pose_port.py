@@ -1,8 +1,8 @@
 """oracle/pose_port.py -- TEST INFRASTRUCTURE ONLY (checker for the pose post-processing rows N2 / N4).
 
 The reference's host code restated as plain functions: `quat2mat` (train.py:762-796), the relative pose
-of one prediction (train.py:875-886: [R|t] then np.linalg.inv) and `convert_to_absolute`, dict branch
-(slam/common/kitti360_utils.py:406-432).  Pinned in tests/test_pose_cpu.py against the reference's own
+of one prediction (train.py:875-886: [R|t] then np.linalg.inv) and `convert_to_absolute`, dict and
+ndarray branches (slam/common/kitti360_utils.py:406-432).  Pinned in tests/test_pose_cpu.py against the reference's own
 `convert_to_absolute` (imported from /root/reference where mounted) and against rotation-matrix identities.
 """
 import numpy as np
@@ -31,9 +31,20 @@ def relative_pose(pred_params, invert=True):
 
 
 def convert_to_absolute(relative_poses, first_transformation=None):
+    """dict branch, kitti360_utils.py:422-427"""
     prev = np.eye(4) if first_transformation is None else first_transformation
     out = []
     for rel in relative_poses:
         prev = np.linalg.inv(rel @ np.linalg.inv(prev))
         out.append(prev)
     return np.stack(out)
+
+
+def convert_to_absolute_array(relative_poses, first_transformation=None):
+    """ndarray branch, kitti360_utils.py:412-420: accumulate rel_i @ prev, invert everything at the end"""
+    prev = np.eye(4) if first_transformation is None else first_transformation
+    out = []
+    for rel in relative_poses:
+        prev = rel @ prev
+        out.append(prev)
+    return np.linalg.inv(np.stack(out))

@@ -36,14 +36,29 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def furthest_point_sampling(points, nsamples, flags=_FPS_FLAGS):
+def furthest_point_sampling(points, nsamples, flags=_FPS_FLAGS, tie_in=None, return_tie=False):
+    """The reference signature is (points, nsamples).  Extension (not in the reference): `return_tie=True` also returns
+    an int32[B] flag per cloud, 1 when the run saw two candidates tie for an arg-max; handing that flag as `tie_in` to
+    the sampling of the SELECTED points (the next pyramid level, P2/pointnet2_modules.py:200-206) lets tie-free clouds
+    return 0..nsamples-1 without the dependent rounds -- bit-identical (include/pwclo_b200.h)."""
     _chk(points, "points", torch.float32)
     B, N, _ = points.shape
     out = torch.zeros((B, nsamples), dtype=torch.int32, device=points.device)
+    if tie_in is None and not return_tie:
+        with torch.cuda.device(points.device):
+            _lib.check(_lib.lib().pwclo_furthest_point_sampling(_p(points), B, N, int(nsamples), int(flags), _p(out),
+                                                                _lib.stream_ptr()), "furthest_point_sampling")
+        return out
+    if tie_in is not None:
+        _chk(tie_in, "tie_in", torch.int32)
+        if tie_in.numel() != B:
+            raise RuntimeError("tie_in must hold one int32 flag per cloud")
+    tie = torch.empty(B, dtype=torch.int32, device=points.device) if return_tie else None
     with torch.cuda.device(points.device):
-        _lib.check(_lib.lib().pwclo_furthest_point_sampling(_p(points), B, N, int(nsamples), int(flags), _p(out),
-                                                            _lib.stream_ptr()), "furthest_point_sampling")
-    return out
+        _lib.check(_lib.lib().pwclo_furthest_point_sampling_prefix(
+            _p(points), B, N, int(nsamples), int(flags), _p(out), _p(tie_in) if tie_in is not None else None,
+            _p(tie) if tie is not None else None, _lib.stream_ptr()), "furthest_point_sampling_prefix")
+    return (out, tie) if return_tie else out
 
 
 def gather_points(points, idx):

@@ -23,6 +23,7 @@ _LP = ctypes.POINTER(LayerT)
 # name -> argtypes  (must list every symbol declared in include/pwclo_b200.h; tests check this)
 SIGNATURES = {
     "pwclo_furthest_point_sampling": [_vp, _i, _i, _i, _u, _vp, _vp],
+    "pwclo_furthest_point_sampling_prefix": [_vp, _i, _i, _i, _u, _vp, _vp, _vp, _vp],
     "pwclo_gather_points": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "pwclo_gather_points_grad": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "pwclo_group_points": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],

@@ -35,10 +35,25 @@ __device__ __forceinline__ unsigned fps_key_to_index(unsigned key, int logT) {
 
 // MODE 0: xyz + mind in registers, MODE 1: xyz in smem, mind in registers, MODE 2: everything in
 // global memory (mind in `scratch`), any n.
-template <int P, int THREADS, int MODE>
+// Prefix property: when the cloud handed to FPS is itself the FPS-ordered output of a run that never saw
+// two candidates tie for the arg-max (`tie_in[b] == 0`), the first m samples of this run are 0, 1, ..., m-1 -- the
+// running minima are the same floats round for round, so the same points win.  Every kernel below starts with this
+// early-out and, when asked (`tie_out`), reports whether its own run saw a tie (conservatively: a set flag may be a
+// false alarm, a clear flag is exact).
+__device__ __forceinline__ bool fps_prefix_shortcut(const int32_t* __restrict__ tie_in, int32_t* __restrict__ tie_out, int b,
+                                                    int m, int32_t* __restrict__ idx, int tid, int threads, bool writer) {
+  if (tie_in == nullptr || tie_in[b] != 0) return false;
+  if (writer) {
+    for (int r = tid; r < m; r += threads) idx[r] = r;
+    if (tie_out != nullptr && tid == 0) tie_out[b] = 0;
+  }
+  return true;
+}
+
+template <int P, int THREADS, int MODE, bool TIE>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origin_skip, float* __restrict__ scratch,
-           int32_t* __restrict__ idx) {
+           int32_t* __restrict__ idx, const int32_t* __restrict__ tie_in, int32_t* __restrict__ tie_out) {
   extern __shared__ float smem[];
   constexpr int NW = THREADS / 32;
   float* sx = smem;
@@ -46,12 +61,15 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origin_ski
   float* sz = sy + (MODE == 2 ? 0 : n);
   __shared__ unsigned red_val[2][32];
   __shared__ unsigned red_key[2][32];
+  __shared__ unsigned red_tie[2][32];
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   xyz += (size_t)b * n * 3;
   idx += (size_t)b * m;
+  if (fps_prefix_shortcut(tie_in, tie_out, b, m, idx, tid, THREADS, true)) return;
+  bool tie_acc = MODE == 2;      // the global-memory fallback does not track ties: always "maybe"
   float* gmind = (MODE == 2) ? scratch + (size_t)b * n : nullptr;
 
   float px[MODE == 0 ? P : 1], py[MODE == 0 ? P : 1], pz[MODE == 0 ? P : 1];
@@ -125,15 +143,32 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origin_ski
     unsigned wv = __reduce_max_sync(PWCLO_FULL_MASK, vb);
     unsigned wk = __reduce_min_sync(PWCLO_FULL_MASK, vb == wv ? key : 0xffffffffu);
     const int buf = r & 1;
+    if (TIE && MODE != 2) {
+      bool lt = false;
+      if (vb == wv && wv != 0u) {
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) c += (mind[j] == best) ? 1 : 0;
+        lt = c > 1;
+      }
+      const bool wt = __popc(__ballot_sync(PWCLO_FULL_MASK, vb == wv)) > 1 || __any_sync(PWCLO_FULL_MASK, lt);
+      if (lane == 0) red_tie[buf][warp] = wt ? 1u : 0u;
+    }
     if (lane == 0) { red_val[buf][warp] = wv; red_key[buf][warp] = wk; }
     __syncthreads();
     unsigned v2 = lane < NW ? red_val[buf][lane] : 0u;
     unsigned k2 = lane < NW ? red_key[buf][lane] : 0xffffffffu;
     unsigned bv = __reduce_max_sync(PWCLO_FULL_MASK, v2);
     unsigned bk = __reduce_min_sync(PWCLO_FULL_MASK, v2 == bv ? k2 : 0xffffffffu);
+    if (TIE && MODE != 2) {
+      const unsigned t2 = lane < NW ? red_tie[buf][lane] : 0u;
+      const unsigned eq = __ballot_sync(PWCLO_FULL_MASK, lane < NW && v2 == bv);
+      tie_acc |= bv == 0u || __popc(eq) > 1 || __any_sync(PWCLO_FULL_MASK, lane < NW && v2 == bv && t2 != 0u);
+    }
     old = bv == 0u ? 0 : (int)fps_key_to_index(bk, logT);
     if (tid == 0) idx[r] = old;
   }
+  if (TIE && tid == 0 && tie_out != nullptr) tie_out[b] = tie_acc ? 1 : 0;
 }
 
 
@@ -187,9 +222,10 @@ __device__ __forceinline__ void fps_bitonic_sort32(unsigned* keys, int tid) {
   }
 }
 
-template <int P, int THREADS>
+template <int P, int THREADS, bool TIE>
 __global__ void __launch_bounds__(THREADS, 1)
-fps_slab_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origin_skip, int32_t* __restrict__ idx, int dbg) {
+fps_slab_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origin_skip, int32_t* __restrict__ idx, int dbg,
+                const int32_t* __restrict__ tie_in, int32_t* __restrict__ tie_out) {
   constexpr int NP = P * THREADS;
   constexpr int NW = THREADS / 32;
   extern __shared__ __align__(16) unsigned char fps_smem[];
@@ -201,11 +237,15 @@ fps_slab_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origi
   __shared__ unsigned red_val[2][32];
   __shared__ unsigned red_key[2][32];
   __shared__ float ext_mn[3][32], ext_mx[3][32];
+  __shared__ unsigned red_tie[2][32];
   __shared__ int axis_s;
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   xyz += (size_t)b * n * 3;
   idx += (size_t)b * m;
+  if (fps_prefix_shortcut(tie_in, tie_out, b, m, idx, tid, THREADS, true)) return;
+  bool tie_acc = false;
+  unsigned wtie = 0u;                   // cached with (wv, wk): the warp's maximum is attained by more than one point
 
   // ---- stage the cloud, pick the widest axis
   float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
@@ -337,26 +377,48 @@ fps_slab_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origi
       if (vb == wv) key = fps_key((unsigned)my_idx[bj * 32], logT);
       wk = __reduce_min_sync(PWCLO_FULL_MASK, key);
       wmax = wv == 0u ? -1.0f : __uint_as_float(wv - 1u);
+      if (TIE) {
+        bool lt = false;
+        if (vb == wv && wv != 0u) {     // the lane(s) holding the warp maximum: is it attained twice inside the thread?
+          int c = 0;
+#pragma unroll
+          for (int j = 0; j < P; ++j) c += (mind[j] == best) ? 1 : 0;
+          lt = c > 1;
+        }
+        wtie = (__popc(__ballot_sync(PWCLO_FULL_MASK, vb == wv)) > 1 || __any_sync(PWCLO_FULL_MASK, lt)) ? 1u : 0u;
+      }
     }
     const int buf = r & 1;
-    if (lane == 0) { red_val[buf][warp] = wv; red_key[buf][warp] = wk; }
+    if (lane == 0) {
+      red_val[buf][warp] = wv; red_key[buf][warp] = wk;
+      if (TIE) red_tie[buf][warp] = wtie;
+    }
     __syncthreads();
     const unsigned v2 = lane < NW ? red_val[buf][lane] : 0u;
     const unsigned k2 = lane < NW ? red_key[buf][lane] : 0xffffffffu;
     const unsigned bv = __reduce_max_sync(PWCLO_FULL_MASK, v2);
     const unsigned bk = __reduce_min_sync(PWCLO_FULL_MASK, v2 == bv ? k2 : 0xffffffffu);
+    if (TIE) {
+      const unsigned t2 = lane < NW ? red_tie[buf][lane] : 0u;
+      const unsigned eq = __ballot_sync(PWCLO_FULL_MASK, lane < NW && v2 == bv);
+      tie_acc |= bv == 0u || __popc(eq) > 1 || __any_sync(PWCLO_FULL_MASK, lane < NW && v2 == bv && t2 != 0u);
+    }
     old = bv == 0u ? 0 : (int)fps_key_to_index(bk, logT);
     if (tid == 0) idx[r] = old;
   }
+  if (TIE && tid == 0 && tie_out != nullptr) tie_out[b] = tie_acc ? 1 : 0;
 }
 
+struct FpsTie { const int32_t* in; int32_t* out; };
+
 template <int P, int THREADS>
-static int launch_fps_slab(const float* xyz, int B, int n, int m, int logT, int origin_skip, int32_t* idx, cudaStream_t st) {
+static int launch_fps_slab(const float* xyz, int B, int n, int m, int logT, int origin_skip, int32_t* idx, FpsTie tie,
+                           cudaStream_t st) {
   const size_t smem = (size_t)P * THREADS * (sizeof(unsigned) + sizeof(int)) + (size_t)3 * n * sizeof(float);
-  auto kern = fps_slab_kernel<P, THREADS>;
+  auto kern = tie.out ? fps_slab_kernel<P, THREADS, true> : fps_slab_kernel<P, THREADS, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  kern<<<B, THREADS, smem, st>>>(xyz, n, m, logT, origin_skip, idx, getenv("PWCLO_FPS_DBG_SKIPALL") ? 1 : 0);
+  kern<<<B, THREADS, smem, st>>>(xyz, n, m, logT, origin_skip, idx, getenv("PWCLO_FPS_DBG_SKIPALL") ? 1 : 0, tie.in, tie.out);
   return launch_status();
 }
 
@@ -374,14 +436,15 @@ namespace cg = cooperative_groups;
 constexpr int kFpsCluster = 8;
 constexpr int kFpsClThreads = 256;
 
-struct FpsCand { unsigned val, key; float x, y, z; };
+struct FpsCand { unsigned val, key; float x, y, z; unsigned tie; };
 
-template <int P>
+template <int P, bool TIE>
 __global__ void __launch_bounds__(kFpsClThreads, 1)
-fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origin_skip, int32_t* __restrict__ idx) {
+fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origin_skip, int32_t* __restrict__ idx,
+                   const int32_t* __restrict__ tie_in, int32_t* __restrict__ tie_out) {
   constexpr int THREADS = kFpsClThreads, CL = kFpsCluster, TT = THREADS * CL, NW = THREADS / 32;
   __shared__ float sx[P * THREADS], sy[P * THREADS], sz[P * THREADS];     // this CTA's points, slot = j*THREADS + tid
-  __shared__ unsigned red_val[2][NW], red_key[2][NW];
+  __shared__ unsigned red_val[2][NW], red_key[2][NW], red_tie[2][NW];
   __shared__ FpsCand cand[2][CL];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -389,6 +452,9 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int logT, int or
   const int gt = rank * THREADS + tid;                 // global thread of the cloud: owns points gt, gt + TT, ...
   xyz += (size_t)b * n * 3;
   idx += (size_t)b * m;
+  // the flag is per cloud, so all CTAs of the cluster take the same branch (no cluster barrier is left half-entered)
+  if (fps_prefix_shortcut(tie_in, tie_out, b, m, idx, tid, THREADS, rank == 0)) return;
+  bool tie_acc = false;
 
   float px[P], py[P], pz[P], mind[P];
 #pragma unroll
@@ -426,6 +492,17 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int logT, int or
     const unsigned wv = __reduce_max_sync(PWCLO_FULL_MASK, vb);
     const unsigned wk = __reduce_min_sync(PWCLO_FULL_MASK, vb == wv ? key : 0xffffffffu);
     const int buf = r & 1;
+    if (TIE) {
+      bool lt = false;
+      if (vb == wv && wv != 0u) {
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) c += (mind[j] == best) ? 1 : 0;
+        lt = c > 1;
+      }
+      const bool wt = __popc(__ballot_sync(PWCLO_FULL_MASK, vb == wv)) > 1 || __any_sync(PWCLO_FULL_MASK, lt);
+      if (lane == 0) red_tie[buf][warp] = wt ? 1u : 0u;
+    }
     if (lane == 0) { red_val[buf][warp] = wv; red_key[buf][warp] = wk; }
     __syncthreads();
     if (warp == 0) {
@@ -433,9 +510,15 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int logT, int or
       const unsigned k2 = lane < NW ? red_key[buf][lane] : 0xffffffffu;
       const unsigned bv = __reduce_max_sync(PWCLO_FULL_MASK, v2);
       const unsigned bk = __reduce_min_sync(PWCLO_FULL_MASK, v2 == bv ? k2 : 0xffffffffu);
+      unsigned ctie = 0u;
+      if (TIE) {
+        const unsigned t2 = lane < NW ? red_tie[buf][lane] : 0u;
+        const unsigned eq = __ballot_sync(PWCLO_FULL_MASK, lane < NW && v2 == bv);
+        ctie = (__popc(eq) > 1 || __any_sync(PWCLO_FULL_MASK, lane < NW && v2 == bv && t2 != 0u)) ? 1u : 0u;
+      }
       if (lane < CL) {
         FpsCand c;
-        c.val = bv; c.key = bk; c.x = 0.f; c.y = 0.f; c.z = 0.f;
+        c.val = bv; c.key = bk; c.x = 0.f; c.y = 0.f; c.z = 0.f; c.tie = ctie;
         if (bv != 0u) {
           const int k = (int)fps_key_to_index(bk, logT);           // a point of this CTA
           const int slot = (k / TT) * THREADS + (k % TT - rank * THREADS);
@@ -452,6 +535,12 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int logT, int or
       const unsigned v = cand[buf][c].val, k = cand[buf][c].key;
       if (v > bv || (v == bv && k < bk)) { bv = v; bk = k; who = c; }
     }
+    if (TIE) {
+      int cnt = 0;
+#pragma unroll
+      for (int c = 0; c < CL; ++c) cnt += (cand[buf][c].val == bv) ? 1 : 0;
+      tie_acc |= bv == 0u || cnt > 1 || cand[buf][who].tie != 0u;
+    }
     int old = 0;
     if (bv != 0u) {
       old = (int)fps_key_to_index(bk, logT);
@@ -461,11 +550,13 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int logT, int or
     }
     if (rank == 0 && tid == 0) idx[r] = old;
   }
+  if (TIE && rank == 0 && tid == 0 && tie_out != nullptr) tie_out[b] = tie_acc ? 1 : 0;
   cluster.sync();        // nobody exits while a neighbour may still write into its slot table
 }
 
 template <int P>
-static int launch_fps_cluster(const float* xyz, int B, int n, int m, int logT, int origin_skip, int32_t* idx, cudaStream_t st) {
+static int launch_fps_cluster(const float* xyz, int B, int n, int m, int logT, int origin_skip, int32_t* idx, FpsTie tie,
+                              cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(kFpsCluster, B, 1);
   cfg.blockDim = dim3(kFpsClThreads, 1, 1);
@@ -478,20 +569,23 @@ static int launch_fps_cluster(const float* xyz, int B, int n, int m, int logT, i
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, fps_cluster_kernel<P>, xyz, n, m, logT, origin_skip, idx);
+  const int32_t* tin = tie.in;
+  int32_t* tout = tie.out;
+  cudaError_t e = tie.out ? cudaLaunchKernelEx(&cfg, fps_cluster_kernel<P, true>, xyz, n, m, logT, origin_skip, idx, tin, tout)
+                          : cudaLaunchKernelEx(&cfg, fps_cluster_kernel<P, false>, xyz, n, m, logT, origin_skip, idx, tin, tout);
   return e == cudaSuccess ? launch_status() : (int)e;
 }
 
 template <int P, int THREADS, int MODE>
 static int launch_fps(const float* xyz, int B, int n, int m, int logT, int origin_skip, float* scratch, int32_t* idx,
-                      cudaStream_t st) {
+                      FpsTie tie, cudaStream_t st) {
   size_t smem = MODE == 2 ? 0 : (size_t)3 * n * sizeof(float);
-  auto kern = fps_kernel<P, THREADS, MODE>;
+  auto kern = tie.out ? fps_kernel<P, THREADS, MODE, true> : fps_kernel<P, THREADS, MODE, false>;
   if (smem > 32 * 1024) {  // static smem (reduction slots) counts against the 48 KB default limit
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  kern<<<B, THREADS, smem, st>>>(xyz, n, m, logT, origin_skip, scratch, idx);
+  kern<<<B, THREADS, smem, st>>>(xyz, n, m, logT, origin_skip, scratch, idx, tie.in, tie.out);
   return launch_status();
 }
 
@@ -503,9 +597,16 @@ using namespace pwclo;
 // path is outside every BASELINE configuration and exists so that no size silently fails.
 PWCLO_API int pwclo_furthest_point_sampling(const float* xyz, int B, int N, int m, unsigned flags, int32_t* idx,
                                             void* stream) {
+  return pwclo_furthest_point_sampling_prefix(xyz, B, N, m, flags, idx, nullptr, nullptr, stream);
+}
+
+PWCLO_API int pwclo_furthest_point_sampling_prefix(const float* xyz, int B, int N, int m, unsigned flags, int32_t* idx,
+                                                   const int32_t* tie_in, int32_t* tie_out, void* stream) {
   if (!xyz || !idx || B < 0 || N <= 0 || m < 0) return PWCLO_EINVAL;
+  if (tie_in && m > N) return PWCLO_EINVAL;        // a prefix of length m needs m input points
   if (B == 0 || m == 0) return PWCLO_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  const FpsTie tie = {tie_in, tie_out};
   const int cap = (flags & PWCLO_FPS_CAP1024) ? 1024 : 512;
   int T = 1, logT = 0;
   while (T * 2 <= N && T * 2 <= cap) { T *= 2; ++logT; }
@@ -520,9 +621,9 @@ PWCLO_API int pwclo_furthest_point_sampling(const float* xyz, int B, int N, int 
     // needs 0.43 us per round and stays the choice (PWCLO_FPS_CLUSTER=2 forces the cluster there, for tests).
     const bool force = ce && ce[0] == '2';
     if (allow && m >= 64 && N >= 2048 && N <= 16384 && (N > 8192 || force) && B * kFpsCluster <= kNumSM) {
-      if (N <= 4096) return launch_fps_cluster<2>(xyz, B, N, m, logT, skip, idx, st);
-      if (N <= 8192) return launch_fps_cluster<4>(xyz, B, N, m, logT, skip, idx, st);
-      return launch_fps_cluster<8>(xyz, B, N, m, logT, skip, idx, st);
+      if (N <= 4096) return launch_fps_cluster<2>(xyz, B, N, m, logT, skip, idx, tie, st);
+      if (N <= 8192) return launch_fps_cluster<4>(xyz, B, N, m, logT, skip, idx, tie, st);
+      return launch_fps_cluster<8>(xyz, B, N, m, logT, skip, idx, tie, st);
     }
   }
   // THREADS must be a multiple of T so that a thread's points share (k mod T): 512 or 1024 (cap 1024)
@@ -531,16 +632,16 @@ PWCLO_API int pwclo_furthest_point_sampling(const float* xyz, int B, int N, int 
   if (m >= 256 && N >= (slab_min ? atoi(slab_min) : 2049) && !getenv("PWCLO_FPS_NO_SLAB")) {
     const bool wide = getenv("PWCLO_FPS_SLAB8") == nullptr;     // 512 threads x 16 points: fewer warps per barrier (7 % faster)
     if (cap == 1024) {
-      if (N <= 4096) return launch_fps_slab<4, 1024>(xyz, B, N, m, logT, skip, idx, st);
-      if (N <= 8192) return launch_fps_slab<8, 1024>(xyz, B, N, m, logT, skip, idx, st);
+      if (N <= 4096) return launch_fps_slab<4, 1024>(xyz, B, N, m, logT, skip, idx, tie, st);
+      if (N <= 8192) return launch_fps_slab<8, 1024>(xyz, B, N, m, logT, skip, idx, tie, st);
     } else {
-      if (N <= 2048) return launch_fps_slab<4, 512>(xyz, B, N, m, logT, skip, idx, st);
-      if (N <= 4096) return launch_fps_slab<8, 512>(xyz, B, N, m, logT, skip, idx, st);
-      if (N <= 8192) return wide ? launch_fps_slab<16, 512>(xyz, B, N, m, logT, skip, idx, st)
-                                 : launch_fps_slab<8, 1024>(xyz, B, N, m, logT, skip, idx, st);
+      if (N <= 2048) return launch_fps_slab<4, 512>(xyz, B, N, m, logT, skip, idx, tie, st);
+      if (N <= 4096) return launch_fps_slab<8, 512>(xyz, B, N, m, logT, skip, idx, tie, st);
+      if (N <= 8192) return wide ? launch_fps_slab<16, 512>(xyz, B, N, m, logT, skip, idx, tie, st)
+                                 : launch_fps_slab<8, 1024>(xyz, B, N, m, logT, skip, idx, tie, st);
     }
   }
-#define FPS_CASE(P, TH, MODE) return launch_fps<P, TH, MODE>(xyz, B, N, m, logT, skip, nullptr, idx, st)
+#define FPS_CASE(P, TH, MODE) return launch_fps<P, TH, MODE>(xyz, B, N, m, logT, skip, nullptr, idx, tie, st)
   if (cap == 1024 || N > 4096) {
     if (N <= 1024) FPS_CASE(1, 1024, 0);
     if (N <= 2048) FPS_CASE(2, 1024, 0);
@@ -558,7 +659,7 @@ PWCLO_API int pwclo_furthest_point_sampling(const float* xyz, int B, int N, int 
   float* scratch = nullptr;
   cudaError_t e = cudaMallocAsync((void**)&scratch, (size_t)B * N * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
-  int rc = launch_fps<1, 1024, 2>(xyz, B, N, m, logT, skip, scratch, idx, st);
+  int rc = launch_fps<1, 1024, 2>(xyz, B, N, m, logT, skip, scratch, idx, tie, st);
   cudaFreeAsync(scratch, st);
   return rc;
 }

@@ -440,11 +440,9 @@ PWCLO_API int pwclo_prepare_scans_crop(const float* raw, const long long* offset
   const size_t smem = (size_t)(kPrepBins * 2 + 2) * 4 + (size_t)(npoints + kPrepBoundaryCap) * 8 +
                       (size_t)(npoints + kPrepCandSlack) * 4;
   if (smem > 226 * 1024) return PWCLO_EUNSUPPORTED;
-  static bool configured = false;
-  if (!configured) {
+  {   // the attribute is per device: set it on every call (as every other launcher here does)
     cudaError_t e = cudaFuncSetAttribute(scan_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
   }
   unsigned short* pref = reinterpret_cast<unsigned short*>(workspace);
   unsigned* ghist = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(workspace) +

@@ -185,7 +185,10 @@ class FusedPWCLONet:
         self.L = {k: A.layers(v) for k, v in self.recs.items() if isinstance(v, list)}
         self.LT = {k: A.layers(v) for k, v in self.tc_recs.items()}
         self.use_tc = os.environ.get("PWCLO_TC", "1") != "0"
+        self.fps_prefix = os.environ.get("PWCLO_FPS_PREFIX", "1") != "0"
         self._sorted = {}
+        self._graphs = {}        # (B, N) -> captured whole-forward CUDA graph (forward_graphed)
+        self.use_graph = os.environ.get("PWCLO_INFER_GRAPH", "1") != "0"
         self.lib = _lib.lib()
         self.launches = 0
         self.verbose_timeline = False
@@ -218,12 +221,19 @@ class FusedPWCLONet:
     def _new(self, *shape, dtype=torch.float32):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
-    def fps(self, xyz, m):
+    def fps(self, xyz, m, tie_in=None):
+        """-> (idx [B,m], tie [B]): `tie` is the per-cloud flag of pwclo_furthest_point_sampling_prefix; handing it to
+        the next level's call lets tie-free clouds return 0..m-1 without their m-1 dependent rounds (same indices)"""
         B, N, _ = xyz.shape
         idx = self._new(B, m, dtype=torch.int32)
-        self._call("pwclo_furthest_point_sampling", _p(xyz), B, N, m, 1, _p(idx),
+        if not self.fps_prefix:
+            self._call("pwclo_furthest_point_sampling", _p(xyz), B, N, m, 1, _p(idx),
+                       note=f"[B{B} N{N} m{m}]" if self.verbose_timeline else "", work=(4 * B * (3 * N + m), 0))
+            return idx, None
+        tie = self._new(B, dtype=torch.int32)
+        self._call("pwclo_furthest_point_sampling_prefix", _p(xyz), B, N, m, 1, _p(idx), _p(tie_in), _p(tie),
                    note=f"[B{B} N{N} m{m}]" if self.verbose_timeline else "", work=(4 * B * (3 * N + m), 0))
-        return idx
+        return idx, tie
 
     def gather3(self, xyz, idx):
         B, N, _ = xyz.shape
@@ -340,10 +350,66 @@ class FusedPWCLONet:
     # ------------------------------------------------------------------ the network
     LEVELS = ((2048, 32), (1024, 32), (256, 16), (64, 16))
 
-    def forward(self, xyz_f1, xyz_f2, trace=None):
+    # ------------------------------------------------------------------ the whole forward as ONE CUDA graph
+    MAX_GRAPHS = 4
+
+    def forward_graphed(self, xyz_f1, xyz_f2):
+        """forward() replayed from a CUDA graph captured once per input shape (every shape on the path is static:
+        the launch list of a forward depends on (B, N) only).  The reference pays ~550 launches and a forced
+        device->host sync per forward (PW/pwclo_net.py:186-193); the fused forward is ~55 launches whose host cost
+        (ctypes + ~60 torch.empty) is what bounds batches of a few pairs -- the sharded batch at 8 GPUs, the odometry
+        adapter at one pair.  Inputs are copied into the graph's static buffers (this replaces forward()'s torch.cat),
+        outputs are cloned out of them, so results stay valid across calls like any torch result."""
+        if (not self.use_graph or self.timeline is not None or self.overlap or not xyz_f1.is_cuda
+                or xyz_f1.dtype != torch.float32 or xyz_f2.dtype != torch.float32 or xyz_f1.shape != xyz_f2.shape):
+            return self.forward(xyz_f1, xyz_f2)
+        key = (xyz_f1.shape[0], xyz_f1.shape[2])
+        rec = self._graphs.get(key)
+        if rec is None:
+            rec = self._capture(xyz_f1, xyz_f2)
+            if len(self._graphs) >= self.MAX_GRAPHS:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = rec
+        if rec is False:                       # capture failed for this shape (reported once): eager launches
+            return self.forward(xyz_f1, xyz_f2)
+        B = key[0]
+        with torch.cuda.device(self.device):
+            rec["in"][:B].copy_(xyz_f1, non_blocking=True)
+            rec["in"][B:].copy_(xyz_f2, non_blocking=True)
+            rec["graph"].replay()
+            self.launches += rec["launches"]
+            return tuple(o.clone() for o in rec["out"])
+
+    def _capture(self, xyz_f1, xyz_f2):
+        B, _, N = xyz_f1.shape
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            static_in = torch.cat((xyz_f1, xyz_f2), dim=0).contiguous().clone()
+            try:
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):             # one eager pass: loads every kernel, sets the smem attributes
+                    self.forward(None, None, _cat=static_in)
+                cur.wait_stream(side)
+                torch.cuda.synchronize(self.device)
+                graph = torch.cuda.CUDAGraph()
+                n0 = self.launches
+                with torch.cuda.graph(graph):
+                    out = self.forward(None, None, _cat=static_in)
+                n = self.launches - n0
+                self.launches = n0
+                return {"in": static_in, "graph": graph, "out": out, "launches": n}
+            except Exception as e:      # the same kernels still run, one launch at a time
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the fused forward failed for B={B}, N={N} ({type(e).__name__}: {e}); "
+                              "this shape runs with eager launches")
+                torch.cuda.synchronize(self.device)
+                return False
+
+    def forward(self, xyz_f1, xyz_f2, trace=None, _cat=None):
         """xyz_f1, xyz_f2: [B,3,N] fp32 CUDA -> (pose_params [B,4,7], embedding_mask_1 [B,64,2048] view,
-        new_xyz_f1_1 [B,2048,3])"""
-        B = xyz_f1.shape[0]
+        new_xyz_f1_1 [B,2048,3]).  _cat: the two frames already stacked as [2B,3,N] (forward_graphed)."""
+        B = xyz_f1.shape[0] if _cat is None else _cat.shape[0] // 2
         self._sorted = {}          # (data_ptr, clouds, points) -> sorted kNN workspace, valid for this forward only
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
@@ -363,13 +429,14 @@ class FusedPWCLONet:
                     main.wait_event(ev)
 
             # siamese pyramid: both frames share the weights -> one batch of 2B clouds per level
-            xyz = self.to_point_major(torch.cat((xyz_f1, xyz_f2), dim=0).float())
+            xyz = self.to_point_major(torch.cat((xyz_f1, xyz_f2), dim=0).float() if _cat is None else _cat)
             if side is not None:
                 side.wait_stream(main)      # inputs are ready; also orders this forward's geometry after the previous forward
             xs, lvl_idx, lvl_ev = [xyz], [], []
             with geo:
+                tie = None
                 for l, (npoint, k) in enumerate(self.LEVELS):
-                    fidx = self.fps(xs[-1], npoint)
+                    fidx, tie = self.fps(xs[-1], npoint, tie)
                     new_xyz = self.gather3(xs[-1], fidx)
                     idx = self.knn(xs[-1], new_xyz, k, keep_sorted=l >= 1)      # levels 1-3 are searched again below
                     lvl_idx.append((fidx, idx))

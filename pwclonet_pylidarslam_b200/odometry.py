@@ -43,16 +43,23 @@ def pose_params_to_matrices(pose_params, invert=True):
     return out
 
 
-def convert_to_absolute(relative_poses, first_transformation=None):
-    """float64 CUDA [F,4,4] relative poses -> [F,4,4] absolute poses: abs_f = inv(rel_f @ inv(abs_{f-1}))
-    (kitti360_utils.py:424-427)."""
+def convert_to_absolute(relative_poses, first_transformation=None, dict_semantics=False):
+    """float64 CUDA [F,4,4] relative poses -> [F,4,4] absolute poses (kitti360_utils.py:406-432).
+
+    The reference treats `first_transformation` differently per input type; the input here is an array, so the
+    default follows its ndarray branch (:412-420):  abs_f = inv(rel_f @ ... @ rel_0 @ first).
+    dict_semantics=True gives the dict branch (:422-427):  abs_f = inv(rel_f @ inv(abs_{f-1})), abs_{-1} = first,
+    i.e. inv(rel_f @ ... @ rel_0 @ inv(first)).  Without a first transformation the two are the same."""
     if not (isinstance(relative_poses, torch.Tensor) and relative_poses.is_cuda and relative_poses.dtype == torch.float64):
         raise RuntimeError("relative_poses must be a float64 CUDA tensor (there is no CPU path)")
     rel = relative_poses.contiguous()
     F = rel.shape[0]
     first = None
     if first_transformation is not None:
-        first = torch.as_tensor(first_transformation, dtype=torch.float64).to(rel.device).contiguous()
+        first = torch.as_tensor(first_transformation, dtype=torch.float64).reshape(4, 4)
+        if not dict_semantics:          # the kernel's scan is seeded with abs_{-1}: inv(first) turns it into the array branch
+            first = torch.linalg.inv(first.cpu())
+        first = first.to(rel.device).contiguous()
     out = torch.empty_like(rel)
     with torch.cuda.device(rel.device):
         _lib.check(_lib.lib().pwclo_accumulate_poses(_p(rel), F, _p(first), _p(out), _lib.stream_ptr()), "accumulate_poses")

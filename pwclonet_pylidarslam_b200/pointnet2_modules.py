@@ -29,14 +29,20 @@ class PointnetSAModulePWCLONet(nn.Module):
         self.mlp_spec = spec
         self.mlp_module = pt_utils.SharedMLP(spec, bn=bn, init=torch.nn.init.xavier_uniform_)
 
-    def geometry(self, xyz: torch.Tensor):
+    def geometry(self, xyz: torch.Tensor, tie_in=None, return_tie=False):
         """the non-differentiable, coordinates-only part of forward: (FPS indices [B,npoint], new_xyz [B,npoint,3],
         neighbour indices [B,npoint,nsample]).  A caller that processes several clouds with this module (the two
-        frames of a pair) can compute it for all of them in one batch and hand slices to forward(geom=...)."""
-        fidx = pointnet2_utils.furthest_point_sample(xyz, self.npoint)
+        frames of a pair) can compute it for all of them in one batch and hand slices to forward(geom=...).
+        tie_in / return_tie: the per-cloud tie flags of `_ext.furthest_point_sampling` -- a pyramid passes the flag of
+        the level that produced `xyz` so that tie-free clouds skip the sampling rounds (same indices)."""
+        if tie_in is None and not return_tie:
+            fidx, tie = pointnet2_utils.furthest_point_sample(xyz, self.npoint), None
+        else:
+            from . import _ext
+            fidx, tie = _ext.furthest_point_sampling(xyz.contiguous(), self.npoint, tie_in=tie_in, return_tie=True)
         new_xyz = pointnet2_utils.gather_operation(xyz.transpose(1, 2).contiguous(), fidx).transpose(1, 2).contiguous()
         _, idx = pt_utils.knn_point(self.nsample, xyz, new_xyz)
-        return fidx, new_xyz, idx
+        return (fidx, new_xyz, idx, tie) if return_tie else (fidx, new_xyz, idx)
 
     def forward(self, xyz: torch.Tensor, features: Optional[torch.Tensor], geom=None):
         """xyz (B,N,3), features (B,C,N) or None -> new_xyz (B,npoint,3), new_features (B,C',npoint)"""

@@ -4,13 +4,19 @@ tensors) and forward contract (PW/pwclo_net.py:32-218):
     pose_params[B,4,7], log_dict = net(xyz_f1[B,3,N], None, xyz_f2[B,3,N], None)
 
 Execution:
-  * `net.eval()` + no grad  -> the fused sm_100a inference engine (`..fused.FusedPWCLONet`): BN folded,
+  * `net.eval()`, xyz-only input that does not require grad (with or without `torch.no_grad()`: the
+    reference's own test path, train.py:348-359 / :806-808, calls the model in eval() with autograd on)
+                             -> the fused sm_100a inference engine (`..fused.FusedPWCLONet`): BN folded,
     one kernel per layer, no grouped tensor ever materialised, no forced device->host sync (the
-    reference's log_dict lives on the CPU, pwclo_net.py:186-193; ours is produced lazily);
+    reference's log_dict lives on the CPU, pwclo_net.py:186-193; ours is produced lazily).  Its output
+    carries no autograd graph; config `eval_autograd=True` keeps the composed path in eval mode for
+    whoever differentiates through an eval() forward;
   * otherwise                -> the autograd composition below (same op order as the reference),
     all sampling / neighbour / grouping ops on the sm_100a kernels.
 """
+import operator
 import warnings
+from collections.abc import Mapping
 from enum import Enum
 
 import torch
@@ -38,23 +44,32 @@ class _Config(dict):
     __getattr__ = dict.get
 
 
-class LazyLog(dict):
-    """log_dict whose CPU tensors are only materialised when read (keeps the forward asynchronous)."""
+class LazyLog(Mapping):
+    """log_dict whose CPU tensors are only materialised when read (keeps the forward asynchronous).  A read-only
+    Mapping over the reference's keys (PW/pwclo_net.py:186-193): `[]`, `.get`, `.items()`, `.values()`, iteration,
+    `len`, `dict(log)` and `**log` all see every key; a value is computed (one device->host copy) the first
+    time it is read and cached."""
 
     def __init__(self, thunks):
-        super().__init__()
         self._thunks = dict(thunks)
+        self._values = {}
 
-    def __missing__(self, key):
-        v = self._thunks[key]()
-        self[key] = v
-        return v
+    def __getitem__(self, key):
+        if key not in self._values:
+            self._values[key] = self._thunks[key]()
+        return self._values[key]
 
-    def keys(self):
-        return self._thunks.keys()
-
-    def __contains__(self, key):
+    def __contains__(self, key):           # Mapping's default would evaluate the thunk
         return key in self._thunks
+
+    def __iter__(self):
+        return iter(self._thunks)
+
+    def __len__(self):
+        return len(self._thunks)
+
+    def __repr__(self):
+        return "LazyLog(" + ", ".join(f"{k}=<{'ready' if k in self._values else 'lazy'}>" for k in self._thunks) + ")"
 
 
 class PWCLONet(nn.Module):
@@ -75,7 +90,9 @@ class PWCLONet(nn.Module):
             warnings.warn("current version of PWCLONet allows predicting only one pose")
         self.nb_levels = config.get("num_out_poses", 4)
         self.use_fused = config.get("use_fused", True)
+        self.eval_autograd = config.get("eval_autograd", False)
         self.lazy_log = config.get("lazy_log", True)
+        self.graph_forward = config.get("graph_forward", True)
 
         self.psa_1 = PointnetSAModulePWCLONet(npoint=2048, nsample=32, mlp=[0, 8, 8, 16], bn=True)
         self.psa_2 = PointnetSAModulePWCLONet(npoint=1024, nsample=32, mlp=[16, 16, 16, 32], bn=True)
@@ -95,28 +112,55 @@ class PWCLONet(nn.Module):
         self.pose_warp_refinement_1 = PoseWarpRefinement(16, 16, 64, 64, radius=0.5, last_pose_estimation=True,
                                                          device=dev, scalar_last=sl)
         self._fused = None
+        self._fused_fp = None
+        # a parent module's load_state_dict recurses through _load_from_state_dict and never calls this module's
+        # load_state_dict: the post hook fires in both cases
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_fused())
 
     # -- fused-engine plumbing ------------------------------------------------------------------
+    def invalidate_fused(self):
+        """drop the folded-weight engine (and its captured graphs): the next eval forward re-folds"""
+        self._fused = None
+        self._fused_fp = None
+        self.__dict__.pop("_fp_tensors", None)
+
     def train(self, mode=True):
-        self._fused = None          # parameters / BN statistics may change: re-fold on next eval forward
+        self.invalidate_fused()     # parameters / BN statistics may change: re-fold on next eval forward
         return super().train(mode)
 
-    def load_state_dict(self, *a, **kw):
-        self._fused = None
-        return super().load_state_dict(*a, **kw)
+    def _apply(self, fn, *a, **kw):       # .to() / .cuda() / .float(): the arena lives on the old device
+        self.invalidate_fused()
+        return super()._apply(fn, *a, **kw)
+
+    def _fingerprint(self):
+        """in-place updates through torch while in eval mode (an optimiser step, `p.add_`, `p.copy_`) bump the
+        tensors' version counters; rebinding `p.data` moves the storage.  Writes that bypass torch altogether
+        (`p.data.add_`, a raw kernel) need invalidate_fused()."""
+        plist = self.__dict__.get("_fp_tensors")
+        if plist is None:               # collected once per engine build (invalidate_fused() drops it)
+            plist = list(self.parameters()) + list(self.buffers())
+            self.__dict__["_fp_tensors"] = plist
+        return (tuple(map(operator.attrgetter("_version"), plist)), plist[0].data_ptr(), plist[-1].data_ptr())
 
     def fused_engine(self):
-        if self._fused is None:
+        fp = self._fingerprint()
+        if self._fused is None or fp != self._fused_fp:
             from ..fused import FusedPWCLONet
             self._fused = FusedPWCLONet(self)
+            self._fused_fp = fp
         return self._fused
 
     # -- forward ----------------------------------------------------------------------------------
     def forward(self, xyz_f1, points_f1, xyz_f2, points_f2, bn_decay=None):
-        fused_ok = (self.use_fused and not self.training and not torch.is_grad_enabled()
+        no_graph_needed = (not torch.is_grad_enabled()) or (
+            not self.eval_autograd and not xyz_f1.requires_grad and not xyz_f2.requires_grad)
+        fused_ok = (self.use_fused and not self.training and no_graph_needed
                     and points_f1 is None and points_f2 is None and xyz_f1.is_cuda)
         if fused_ok:
-            pose, mask1, xyz1_l1 = self.fused_engine().forward(xyz_f1, xyz_f2)
+            with torch.no_grad():
+                eng = self.fused_engine()
+                run = eng.forward_graphed if self.graph_forward else eng.forward
+                pose, mask1, xyz1_l1 = run(xyz_f1, xyz_f2)
         else:
             pose, mask1, xyz1_l1 = self._forward_composed(xyz_f1, points_f1, xyz_f2, points_f2)
         thunks = {
@@ -139,9 +183,10 @@ class PWCLONet(nn.Module):
         # calls: train-mode BatchNorm statistics must be those of one frame's batch, as in the reference.
         Bp = xyz_f1_t.shape[0]
         geoms, cur = [], torch.cat((xyz_f1_t, xyz_f2_t), dim=0).detach()
+        tie = None          # FPS of an FPS-ordered, tie-free cloud is 0..m-1: levels 2-4 skip their rounds (same indices)
         for psa in (self.psa_1, self.psa_2, self.psa_3, self.psa_4):
-            g = psa.geometry(cur)
-            geoms.append(g)
+            *g, tie = psa.geometry(cur, tie_in=tie, return_tie=True)
+            geoms.append(tuple(g))
             cur = g[1]
         for psa, g in zip((self.psa_1, self.psa_2, self.psa_3, self.psa_4), geoms):
             a, b = psa(x1[-1], f1[-1], geom=tuple(t[:Bp] for t in g))

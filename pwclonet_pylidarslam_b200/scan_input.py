@@ -53,10 +53,19 @@ def kitti360_crop(near_treshold=30.0, velodyne_height=1.73, wheel_axis_height=0.
 IDENTITY_TR = np.ascontiguousarray(np.eye(4)[:3], np.float64)
 
 
-def prepare_scans(raw, offsets, Tr, npoints, seed, post=None, max_points=None, return_index=False, crop=KITTI_ODOMETRY_CROP):
+MAX_SCAN_POINTS = 1 << 20     # the select kernel's candidate slack (2048 beyond npoints) covers scans up to ~2M points
+
+
+def prepare_scans(raw, offsets, Tr, npoints, seed, post=None, max_points=None, return_index=False, crop=KITTI_ODOMETRY_CROP,
+                  check=False):
     """(`max_points` is accepted for compatibility and ignored.)
     raw float32 [total,4] CUDA, offsets int64 [S+1] CUDA, Tr float64 [3,4] (or [S,3,4]) CUDA ->
-    clouds float32 [S,npoints,3] (+ int32 [S,npoints] source rows, int32 [S] survivors)."""
+    clouds float32 [S,npoints,3] (+ int32 [S,npoints] source rows, int32 [S] survivors).
+
+    Scans with fewer than `npoints` survivors are completed by draws with replacement, as the reference does
+    (kitti_odometry_dataset.py:164-165).  A scan so large that the select kernel's candidate / boundary lists overflow
+    (> ~2M points; KITTI scans have ~1.2e5) is reported as survivors[scan] = -1 and the rows it could not fill stay
+    zero, never uninitialised memory.  `check=True` reads the flags back (one device->host sync) and raises instead."""
     for t, name, dt in ((raw, "raw", torch.float32), (offsets, "offsets", torch.int64), (Tr, "Tr", torch.float64)):
         if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dt and t.is_contiguous()):
             raise RuntimeError(f"{name} must be a contiguous {dt} CUDA tensor (there is no CPU path)")
@@ -69,8 +78,10 @@ def prepare_scans(raw, offsets, Tr, npoints, seed, post=None, max_points=None, r
     total = int(raw.shape[0])
     L = _lib.lib()
     ws = torch.empty(max(16, L.pwclo_prepare_scans_workspace_bytes(total, S)), dtype=torch.uint8, device=raw.device)
-    out = torch.empty((S, npoints, 3), dtype=torch.float32, device=raw.device)
-    idx = torch.empty((S, npoints), dtype=torch.int32, device=raw.device)
+    if S == 1 and total > 2 * MAX_SCAN_POINTS:
+        raise RuntimeError(f"a scan of {total} points is outside what the select kernel supports ({2 * MAX_SCAN_POINTS})")
+    out = torch.zeros((S, npoints, 3), dtype=torch.float32, device=raw.device)
+    idx = torch.zeros((S, npoints), dtype=torch.int32, device=raw.device)
     surv = torch.empty((S,), dtype=torch.int32, device=raw.device)
     p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
     with torch.cuda.device(raw.device):
@@ -78,6 +89,10 @@ def prepare_scans(raw, offsets, Tr, npoints, seed, post=None, max_points=None, r
                                               ctypes.c_ulonglong(int(seed) & (2 ** 64 - 1)), int(npoints), int(crop[0]),
                                               int(crop[1]), float(crop[2]), int(crop[3]), int(crop[4]), float(crop[5]),
                                               p(out), p(idx), p(surv), p(ws), ws.numel(), _lib.stream_ptr()), "prepare_scans")
+    if check:
+        bad = torch.nonzero(surv < 0).flatten().tolist()
+        if bad:
+            raise RuntimeError(f"prepare_scans: scans {bad[:8]} overflow the selection lists of the kernel (too many points)")
     return (out, idx, surv) if return_index else out
 
 
@@ -101,6 +116,9 @@ def prepare_pairs_from_files(files_current, files_previous, Tr, npoints, seed, d
     cur = [load_kitti_bin(p) for p in files_current]
     prev = [load_kitti_bin(p) for p in files_previous]
     buf, off, _ = pack_pairs(cur, prev)
+    biggest = int((off[1:] - off[:-1]).max()) if off.numel() > 1 else 0
+    if biggest > 2 * MAX_SCAN_POINTS:       # offsets are still on the host here: refuse before any kernel runs
+        raise RuntimeError(f"a scan of {biggest} points is outside what the select kernel supports ({2 * MAX_SCAN_POINTS})")
     Tr = np.ascontiguousarray(np.asarray(Tr, np.float64)[:3, :4])
     clouds = prepare_scans(buf.to(dev, non_blocking=True), off.to(dev), torch.from_numpy(Tr).to(dev), npoints, seed,
                            post=post, crop=crop)

@@ -74,3 +74,83 @@ def test_pose_pipeline_equals_direct_forward(cuda):
     assert len(got) == 5
     for a, b in zip(got, direct):
         assert torch.equal(a, b)
+
+
+def _rand_net(cuda, seed, **cfg):
+    from pwclonet_pylidarslam_b200.pwclonet import PWCLONet
+    net = PWCLONet({"device": "cuda:0", **cfg})
+    w = C.weights_for({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    return net.to(cuda).eval(), w
+
+
+def test_graphed_forward_equals_eager_forward(cuda):
+    """the whole forward replayed from one CUDA graph (FusedPWCLONet.forward_graphed) returns bit for bit what the
+    launch-by-launch forward returns, for several shapes and for fresh inputs on every replay; results of earlier
+    calls stay valid after later calls (outputs are cloned out of the graph's static buffers)"""
+    from pwclonet_pylidarslam_b200 import synthetic as syn
+    net, _ = _rand_net(cuda, 4)
+    eng = net.fused_engine()
+    kept = []
+    for B, N, first in ((1, 8192, 500), (3, 8192, 510), (1, 8192, 520), (2, 4096, 530), (3, 8192, 540)):
+        x1, x2, _ = syn.make_batch(first, B, N)
+        a, b = torch.from_numpy(x1).to(cuda), torch.from_numpy(x2).to(cuda)
+        with torch.no_grad():
+            pe, me, xe = eng.forward(a, b)
+            pg, log = net(a, None, b, None)                  # the module's default eval path: graphed
+        assert eng._graphs.get((B, N)) not in (None, False), "graph capture did not happen"
+        assert torch.equal(pe, pg)
+        assert torch.equal(log["point_cloud"], xe.cpu())
+        kept.append((pg, pe.clone()))
+    for pg, pe in kept:
+        assert torch.equal(pg, pe)
+    assert eng.launches > 0
+
+
+def test_eval_forward_without_no_grad_takes_the_fused_engine(cuda):
+    """the reference's test path calls the model in eval() with autograd enabled (train.py:348-359, :806-808):
+    it must get the fused engine, not silently the composed torch path; `eval_autograd=True` keeps the graph"""
+    from pwclonet_pylidarslam_b200 import synthetic as syn
+    net, _ = _rand_net(cuda, 6)
+    x1, x2, _ = syn.make_batch(700, 1, 8192)
+    a, b = torch.from_numpy(x1).to(cuda), torch.from_numpy(x2).to(cuda)
+    n0 = net.fused_engine().launches
+    pose, _ = net(a, None, b, None)                          # grad mode is ON here
+    assert net.fused_engine().launches > n0 and not pose.requires_grad
+    with torch.no_grad():
+        want, _ = net(a, None, b, None)
+    assert torch.equal(pose, want)
+    net2, _ = _rand_net(cuda, 6, eval_autograd=True)
+    pose2, _ = net2(a, None, b, None)
+    assert pose2.requires_grad and net2._fused is None
+    te, re_ = C.pose_errors(pose2.detach().cpu().numpy(), want.cpu().numpy())
+    assert te <= C.TOL_TRANSLATION_M and re_ <= C.TOL_ROTATION_RAD
+
+
+def test_fused_cache_follows_the_weights(cuda):
+    """eval forward -> new weights through a PARENT module's load_state_dict (the trainer's checkpoint
+    path), through .to(), through an in-place torch update -> the next eval forward must use the new weights"""
+    from pwclonet_pylidarslam_b200 import synthetic as syn
+    from pwclonet_pylidarslam_b200.training import _PWCLONetPredictionModule
+    x1, x2, _ = syn.make_batch(710, 1, 8192)
+    a, b = torch.from_numpy(x1).to(cuda), torch.from_numpy(x2).to(cuda)
+    parent = _PWCLONetPredictionModule({"device": "cuda:0"}).to(cuda).eval()
+    net = parent.pwclonet
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    w1, w2 = C.weights_for(shapes, 11), C.weights_for(shapes, 12)
+    fresh = {}
+    for tag, w in (("w1", w1), ("w2", w2)):
+        f, _ = _rand_net(cuda, 11 if tag == "w1" else 12)
+        with torch.no_grad():
+            fresh[tag] = f(a, None, b, None)[0]
+    assert not torch.equal(fresh["w1"], fresh["w2"])
+    parent.load_state_dict({"pwclonet." + k: torch.from_numpy(v) for k, v in w1.items()})
+    with torch.no_grad():
+        assert torch.equal(net(a, None, b, None)[0], fresh["w1"])
+        parent.load_state_dict({"pwclonet." + k: torch.from_numpy(v) for k, v in w2.items()})      # parent recursion
+        assert torch.equal(net(a, None, b, None)[0], fresh["w2"])
+        for k, p in net.state_dict().items():                                                    # in-place torch update
+            p.copy_(torch.from_numpy(w1[k]))
+        assert torch.equal(net(a, None, b, None)[0], fresh["w1"])
+        parent.float().to(cuda)                                                                  # _apply
+        assert net._fused is None

@@ -57,6 +57,59 @@ def test_fps_bit_exact(cuda, ref_ext, B, N, m, kind):
         np.testing.assert_array_equal(got, ref)
 
 
+PREFIX_CASES = [
+    # (B, N, kind, cluster): the pyramid chain N -> 2048|N/4 -> /2 -> /4 -> /4 of PW/pwclo_net.py:66-69 on every input kind
+    (3, 8192, "lidar", "0"), (2, 8192, "rand", "0"), (2, 8192, "dups", "0"), (2, 8192, "origin", "0"), (1, 4096, "grid", "0"),
+    (2, 4096, "rand", "0"), (2, 16384, "lidar", "1"), (2, 16384, "dups", "1"), (2, 4096, "dups", "2"), (2, 4096, "rand", "2"),
+    (2, 700, "rand", "0"), (2, 700, "dups", "0"),
+]
+
+
+@pytest.mark.parametrize("B,N,kind,cluster", PREFIX_CASES)
+def test_fps_prefix_chain_bit_exact(cuda, monkeypatch, B, N, kind, cluster):
+    """pwclo_furthest_point_sampling_prefix along a pyramid: every level equals the plain sampling of the same cloud
+    (C oracle) bit for bit, whether the level took the 0..m-1 shortcut (tie-free clouds) or really ran (tie flag set);
+    tie-free random clouds must take the shortcut (flag 0), duplicated / lattice clouds must raise the flag."""
+    monkeypatch.setenv("PWCLO_FPS_CLUSTER", cluster)
+    x = _fps_input(kind, B, N, seed=3 * N + len(kind))
+    if kind == "rand" and B > 1:
+        x[1, N // 2:] = x[1, :N - N // 2]          # a batch that mixes a tie-free cloud with a duplicated one
+    cur, tie = _dev(x, cuda), None
+    m = max(N // 4, 16)
+    ties = []
+    for div in (1, 2, 4, 4):
+        m = max(m // div, 4)
+        got, tie_out = _ext.furthest_point_sampling(cur, m, tie_in=tie, return_tie=True)
+        want = cpu_ops.fps(cur.cpu().numpy(), m, origin_skip=True, thread_cap=512)
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
+        plain = _ext.furthest_point_sampling(cur, m)
+        assert torch.equal(plain, got)
+        ties.append(tie_out.cpu().numpy().copy())
+        cur = torch.gather(cur, 1, got.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+        tie = tie_out
+    t0 = ties[0]
+    if kind in ("lidar",) or (kind == "rand" and B == 1):
+        assert not t0.any(), "a generic cloud raised the tie flag (the shortcut would never be taken)"
+    if kind == "rand" and B > 1:
+        assert t0[0] == 0 and t0[1] == 1
+    if kind in ("dups", "grid"):
+        assert t0.all()
+    for a, b in zip(ties[:-1], ties[1:]):     # a clear flag stays clear down the chain
+        assert not (b & ~a.astype(bool)).any()
+
+
+def test_fps_prefix_shortcut_is_taken(cuda):
+    """with a clear flag the kernel must not sample at all: hand it a cloud that is NOT FPS-ordered together with a
+    clear flag and it returns 0..m-1 (which proves levels 2-4 of a tie-free pyramid cost no sampling rounds)"""
+    rng = np.random.default_rng(0)
+    x = _dev(_rand_cloud(rng, 2, 2048), cuda)
+    flag = torch.tensor([0, 1], dtype=torch.int32, device=cuda)
+    got = _ext.furthest_point_sampling(x, 256, tie_in=flag).cpu().numpy()
+    want = cpu_ops.fps(x.cpu().numpy(), 256, origin_skip=True, thread_cap=512)
+    np.testing.assert_array_equal(got[0], np.arange(256))
+    np.testing.assert_array_equal(got[1], want[1])
+
+
 @pytest.mark.parametrize("B,N,m,kind", [(2, 8192, 1024, "rand"), (2, 1500, 400, "dups"), (1, 512, 100, "origin")])
 def test_fps_orphan_variant(cuda, B, N, m, kind):
     """/sampling_gpu_copy.cu: 1024-thread tie order, origin test disabled."""

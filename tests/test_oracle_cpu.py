@@ -46,6 +46,38 @@ def test_fps_properties():
     assert cpu_ops.fps(y, 2)[0, 1] == 6
 
 
+def test_fps_prefix_property_holds_in_the_checker():
+    """SURVEY 0.8, the fact pwclo_furthest_point_sampling_prefix rests on: FPS of the FPS-ordered output of a tie-free
+    run returns 0..m-1 (restated reference kernel, EXT/src/sampling_gpu.cu:85-172), at every nested level of the pyramid;
+    duplicated points (exact ties) break it, which is why the kernels carry a tie flag."""
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((2, 4096, 3)) * np.array([20, 2, 20])).astype(np.float32)
+    cur = x
+    for m in (1024, 512, 128, 32):
+        i = cpu_ops.fps(cur, m)
+        if cur is not x:
+            np.testing.assert_array_equal(i, np.broadcast_to(np.arange(m, dtype=np.int32), i.shape))
+        cur = np.take_along_axis(cur, i[..., None].astype(np.int64), axis=1)
+    y = x.copy()
+    y[:, 2048:] = y[:, :2048]                     # every point twice: the nested run must NOT be 0..m-1 everywhere
+    i1 = cpu_ops.fps(y, 4096)
+    lvl1 = np.take_along_axis(y, i1[..., None].astype(np.int64), axis=1)
+    i2 = cpu_ops.fps(lvl1, 4096)
+    assert (i2 != np.arange(4096)).any()
+
+
+def test_lazy_log_is_a_full_mapping():
+    """log_dict contract of PW/pwclo_net.py:186-193: a reader may use [], get, items, values, iteration, len, dict(), **"""
+    from pwclonet_pylidarslam_b200.pwclonet.pwclo_net import LazyLog
+    calls = []
+    log = LazyLog({"embedding_mask": lambda: calls.append("m") or 1, "point_cloud": lambda: calls.append("p") or 2})
+    assert len(log) == 2 and list(log) == ["embedding_mask", "point_cloud"] and "point_cloud" in log and calls == []
+    assert log.get("embedding_mask") == 1 and log.get("nope", 7) == 7 and calls == ["m"]
+    assert dict(log) == {"embedding_mask": 1, "point_cloud": 2} and calls == ["m", "p"]
+    assert sorted(log.items()) == [("embedding_mask", 1), ("point_cloud", 2)] and list(log.values()) == [1, 2]
+    assert (lambda **kw: kw)(**log) == {"embedding_mask": 1, "point_cloud": 2} and calls == ["m", "p"]
+
+
 def test_knn_matches_torch_cpu_formulation():
     """the oracle's order-0 squared sums are bit-identical to the reference's torch expression on CPU;
     torch's CPU sqrt (MKL VML) is 1 ulp low on ~0.6 % of inputs, the oracle (like torch CUDA, which

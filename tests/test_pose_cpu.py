@@ -41,6 +41,16 @@ def test_convert_to_absolute_equals_reference():
     got = P.convert_to_absolute([rel[i] for i in range(50)])
     for i in range(50):
         np.testing.assert_array_equal(got[i], want[i])
+    # ndarray branch, with and without a non-identity first transformation (the two branches differ there)
+    arr = np.stack([rel[i] for i in range(50)])
+    first = P.relative_pose(np.array([0.3, -0.2, 1.5, 0.98, 0.05, -0.1, 0.02], np.float32))
+    np.testing.assert_array_equal(P.convert_to_absolute_array(arr), ref(arr))
+    np.testing.assert_array_equal(P.convert_to_absolute_array(arr, first), ref(arr, first))
+    wd = ref(rel, first)
+    gd = P.convert_to_absolute([rel[i] for i in range(50)], first)
+    for i in range(50):
+        np.testing.assert_array_equal(gd[i], wd[i])
+    assert np.abs(gd - P.convert_to_absolute_array(arr, first)).max() > 1e-3      # genuinely different semantics
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not mounted")

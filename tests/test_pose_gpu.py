@@ -41,8 +41,11 @@ def test_accumulate_poses(cuda, F):
     scale = max(1.0, np.abs(want).max())
     assert np.abs(got - want).max() <= 1e-11 * scale
     first = P.relative_pose(_params(1, 99)[0, 0])
-    got = O.convert_to_absolute(torch.from_numpy(rel).to(cuda), first).cpu().numpy()
+    got = O.convert_to_absolute(torch.from_numpy(rel).to(cuda), first, dict_semantics=True).cpu().numpy()
     assert np.abs(got - P.convert_to_absolute(rel, first)).max() <= 1e-11 * scale
+    # default = the reference's ndarray branch (the input IS an array): inv(rel_f ... rel_0 @ first)
+    got = O.convert_to_absolute(torch.from_numpy(rel).to(cuda), first).cpu().numpy()
+    assert np.abs(got - P.convert_to_absolute_array(rel, first)).max() <= 1e-10 * scale
 
 
 def test_odometry_adapter(cuda):
