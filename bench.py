@@ -5,18 +5,26 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one inference forward of the hot path (PWCLONet.forward, reference
-slam/models/PWCLONet/pwclo_net.py:109-207) over one batch of synthetic KITTI-64-beam-shaped frame
-pairs: BASELINE.json config "full 4-level hierarchical pose warp-refinement forward, batch 64 frame
-pairs", 64 pairs PER GPU (weak scaling: frame pairs are independent units, no data-path collective).
+slam/models/PWCLONet/pwclo_net.py:109-207) over BASELINE.json config 4: the full 4-level hierarchical pose
+warp-refinement forward on a batch of 64 synthetic KITTI-64-beam-shaped frame pairs, SHARDED over the N GPUs
+(64/N pairs per GPU; frame pairs are independent units, no data-path collective) -> "scaling": "strong".
 
-  value      frame pairs/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  value      frame pairs/s, whole job (64 pairs per step over all ranks), inputs resident in HBM, CUDA-event timed,
+             max over ranks
   e2e        same metric through the public streaming API (sharding.PosePipeline) with inputs in pinned HOST
-             memory: every step's H2D copy of the two clouds and D2H read of pose_params inside the timed
+             memory: every step's H2D copy of the rank's two clouds and D2H read of pose_params inside the timed
              region, the copy of step i+1 overlapping the forward of step i
-  roofline   the dominant kernel of the step, timed live with CUDA events on the launching stream
+  roofline   the dominant kernel of the step on rank 0, timed live with CUDA events on the launching stream
   cpu_baseline  the oracle port of the reference forward (oracle/pwclo_port.py, validated bit-exact
-             against the unmodified reference) on this box's host cores, bounded sample
-  --impl reference  times that same CPU implementation as its own arm (rank 0 only)
+             against the unmodified reference) on this box's host cores, bounded sample (N = 1 only)
+  extra keys (never the headline):
+    weak     N > 1: replicas with 64 pairs PER GPU (what round 1 reported)
+    latency  N = 1: one forward at 1 / 8 / 64 pairs, CUDA graph replay and launch-by-launch
+    train    BASELINE config 5: training step (forward + backward + ONE NCCL all-reduce + Adam), 8 pairs x 16384
+             points per GPU, whole step replayed as one CUDA graph on every rank
+    config2  N = 1: BASELINE config 2, the PointNet++ op suite at batch 8 (FPS / gather / kNN / group)
+    config3  N = 1: BASELINE config 3, the 4 cost volumes + 6 set-upconvs inside a forward of 16 pairs
+  --impl reference  times the CPU implementation of the path as its own arm (rank 0 only)
 """
 import argparse
 import json
@@ -36,6 +44,7 @@ METRIC = "PWCLO-Net frame-pairs/s (8192 pts)"
 UNIT = "frame-pairs/s"
 N_POINTS = 8192
 FLOP_PER_PAIR = 6.04e9   # 3.018 G MACs of shared-MLP work per frame pair
+EXTRAS = ("weak", "latency", "train", "config2", "config3")
 
 
 def parse():
@@ -44,12 +53,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs-per-gpu", type=int, default=64)
-    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs generated per rank")
+    ap.add_argument("--total-pairs", type=int, default=64, help="BASELINE config 4: frame pairs per step over ALL GPUs")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: --total-pairs sharded over the GPUs (default); weak: --total-pairs on EVERY GPU")
+    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic scenes in the batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", default=",".join(EXTRAS), help="comma list of extra keys to measure (or 'none')")
+    ap.add_argument("--extras-timeout", type=float, default=240.0,
+                    help="seconds after which the line is printed without the unfinished extra keys")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
-                    help="train = BASELINE config 5: forward+backward+all-reduce+Adam, 8 pairs per GPU x 16384 points")
-    ap.add_argument("--no-graph", action="store_true", help="train mode: eager step instead of the captured CUDA graph")
+                    help="train = BASELINE config 5 as the headline line: forward+backward+all-reduce+Adam")
+    ap.add_argument("--no-graph", action="store_true", help="train: eager step instead of the captured CUDA graph")
     ap.add_argument("--train-points", type=int, default=16384)
     ap.add_argument("--train-pairs-per-gpu", type=int, default=8)
     return ap.parse_args()
@@ -74,32 +88,36 @@ def ncu_traffic():
     return d.get("families", {}), os.path.relpath(files[-1], ROOT)
 
 
-def _gen_pair(seed):
+def _gen_pair(args):
     from pwclonet_pylidarslam_b200 import synthetic as syn
-    p = syn.make_pair(seed, N_POINTS)
+    seed, n = args
+    p = syn.make_pair(seed, n)
     return p["pc1"], p["pc2"]
 
 
-def make_inputs(rank, pairs, distinct):
-    """`pairs` frame pairs [pairs,3,N] x2: `distinct` ray-cast scenes, replicated with a per-copy yaw
-    (a rigid motion applied to both frames keeps the pair's relative pose and the cloud statistics)."""
+def make_inputs(seed_offset, pairs, distinct, n_points=None, lo=0, hi=None):
+    """Pairs [lo, hi) of a deterministic batch of `pairs` frame pairs -> ([hi-lo,3,N], [hi-lo,3,N]): `distinct` ray-cast
+    scenes, replicated with a per-copy yaw (a rigid motion applied to both frames keeps the pair's relative pose and
+    the cloud statistics).  Every rank can build any slice of the same global batch."""
     from concurrent.futures import ProcessPoolExecutor
     from pwclonet_pylidarslam_b200 import synthetic as syn
+    n_points = n_points or N_POINTS
+    hi = pairs if hi is None else hi
     distinct = min(distinct, pairs)
-    seeds = [syn.SEED_BASE + 1000 * rank + i for i in range(distinct)]
-    workers = max(1, min(distinct, (os.cpu_count() or 2) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
+    need = sorted({i % distinct for i in range(lo, hi)})
+    seeds = [(syn.SEED_BASE + 1000 * seed_offset + s, n_points) for s in need]
+    workers = max(1, min(len(seeds), (os.cpu_count() or 2) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
     if workers > 1:
         with ProcessPoolExecutor(workers) as ex:
-            got = list(ex.map(_gen_pair, seeds))
+            got = dict(zip(need, ex.map(_gen_pair, seeds)))
     else:
-        got = [_gen_pair(s) for s in seeds]
-    rng = np.random.default_rng(rank)
+        got = {s: _gen_pair(a) for s, a in zip(need, seeds)}
+    yaws = np.random.default_rng(seed_offset).uniform(0, 2 * np.pi, size=pairs)
     x1, x2 = [], []
-    for i in range(pairs):
+    for i in range(lo, hi):
         a, b = got[i % distinct]
         if i >= distinct:
-            yaw = rng.uniform(0, 2 * np.pi)
-            c, s = np.cos(yaw), np.sin(yaw)
+            c, s = np.cos(yaws[i]), np.sin(yaws[i])
             R = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], np.float32)
             a, b = a @ R.T, b @ R.T
         x1.append(a.T)
@@ -186,41 +204,322 @@ def cpu_reference(weights, steps, warmup, pairs_per_step=1):
 
 
 def run_reference(args, rank):
+    """--impl reference: the CPU implementation of the path (oracle port, checked bit-exact against the unmodified
+    reference) on all host cores; a step is a bounded sample of the workload -- ONE frame pair of the 64-pair batch
+    (0.65 s on 16 cores) -- so that the driver's --steps / --warmup are honoured as given."""
     if rank != 0:
         return
     w = make_weights()
-    steps = max(1, min(args.steps, 8))
-    v, ms, sample = cpu_reference(w, steps, max(1, min(args.warmup, 2)))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    v, ms, sample = cpu_reference(w, steps, warmup)
     cores = os.cpu_count() or 1
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "PWCLO-Net inference forward, 8192-point synthetic KITTI-64-beam frame pairs, "
                                    "reference CPU path (oracle port of the reference forward; the reference's CUDA "
-                                   "extension has no CPU path), 1 pair per step"},
+                                   "extension has no CPU path), bounded sample: 1 pair of the 64-pair batch per step"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "host": host_info()},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def run_train(args, world, rank, local):
-    """BASELINE config 5: training step = zero_grad, forward (train-mode BN, dropout), loss,
-    backward, ONE NCCL all-reduce of the flat gradient arena, one-launch Adam; `--train-pairs-per-gpu`
-    pairs of `--train-points` points per GPU (weak scaling).  Reports pairs/s and the all-reduce time."""
-    global N_POINTS
-    N_POINTS = args.train_points
-    P = args.train_pairs_per_gpu
-    h1, h2 = make_inputs(rank, P, P)
-    import torch.distributed as dist
-    from pwclonet_pylidarslam_b200 import _lib
+# ------------------------------------------------------------------------------------------------- helpers
+class Ctx:
+    """per-process CUDA / process-group context shared by the measurements"""
+
+    def __init__(self, world, rank, local):
+        import torch.distributed as dist
+        self.world, self.rank, self.local, self.dist = world, rank, local, dist
+        torch.cuda.set_device(local)
+        self.dev = torch.device("cuda", local)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)   # > 126 MB L2
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = torch.tensor(list(values), dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def timed(self, fn, steps):
+        """K steps, L2 flushed before each (outside the events), CUDA events on the launching stream -> (sum ms, last out)"""
+        evs, out = [], None
+        for _ in range(steps):
+            self.flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn()
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs), out
+
+
+def build_net(dev, weights):
+    from pwclonet_pylidarslam_b200.pwclonet import PWCLONet
+    net = PWCLONet({"device": str(dev)})
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    return net.to(dev).eval()
+
+
+def measure_forward(ctx, net, h1, h2, steps, warmup, pairs_total):
+    """resident-input throughput + streaming e2e for this rank's shard (h1, h2 host arrays [p,3,N]); every rank calls it.
+    Returns dict(ms_total, ms_e2e, ms_e2e_serial, launches, pose, pin bytes) with times already max-reduced."""
+    from pwclonet_pylidarslam_b200.sharding import PosePipeline
+    dev = ctx.dev
+    pin1, pin2 = torch.from_numpy(h1).pin_memory(), torch.from_numpy(h2).pin_memory()
+    d1, d2 = pin1.to(dev), pin2.to(dev)
+    eng = net.fused_engine()
+
+    def step_resident():
+        with torch.no_grad():
+            return net(d1, None, d2, None)[0]
+
+    def step_e2e():
+        with torch.no_grad():
+            a = pin1.to(dev, non_blocking=True)
+            b = pin2.to(dev, non_blocking=True)
+            return net(a, None, b, None)[0].cpu()
+
+    for _ in range(max(3, warmup)):
+        step_resident()
+    sampler = ClockSampler(ctx.local)
+    ctx.barrier()
+    sampler.start()
+    launches0 = eng.launches
+    ms_total, pose = ctx.timed(step_resident, steps)
+    launches = eng.launches - launches0
+    ctx.barrier()
+    sampler.stop_flag = True
+    # e2e: the streaming public API (sharding.PosePipeline): every step's two clouds are copied from pinned host
+    # memory and its pose is read back to the host inside the timed region; the copy of step i+1 overlaps the
+    # forward of step i.  The L2 flush between steps is inside the timed region here (it cannot be bracketed out
+    # of an overlapped pipeline), so this number is slightly conservative.
+    pipe = PosePipeline(net, h1.shape[0], h1.shape[2])
+
+    def host_batches(k):
+        for _ in range(k):
+            ctx.flush.zero_()
+            yield pin1, pin2
+
+    for _ in pipe.run(host_batches(3)):
+        pass
+    ctx.barrier()
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_ev.record()
+    for _pose_h in pipe.run(host_batches(steps)):
+        pass
+    e_ev.record()
+    torch.cuda.synchronize()
+    ms_e2e = s_ev.elapsed_time(e_ev)
+    ctx.barrier()
+    step_e2e()
+    ms_e2e_serial, _ = ctx.timed(step_e2e, steps)      # copy -> forward -> read back, nothing overlapped
+    ctx.barrier()
+    ms_total_max, ms_e2e_max, ms_serial_max = ctx.max_over_ranks([ms_total, ms_e2e, ms_e2e_serial])
+    return {"ms_total": ms_total_max, "ms_e2e": ms_e2e_max, "ms_e2e_serial": ms_serial_max, "ms_total_rank": ms_total,
+            "launches": int(launches), "pose": pose, "h2d": int(pin1.numel() * 4 * 2), "d2h": int(pose.numel() * 4),
+            "clocks": sampler.summary(), "step_resident": step_resident,
+            "value": pairs_total * steps / (ms_total_max * 1e-3), "e2e": pairs_total * steps / (ms_e2e_max * 1e-3),
+            "e2e_serial": pairs_total * steps / (ms_serial_max * 1e-3)}
+
+
+def kernel_timeline(net, step_resident):
+    """CUDA events around every launch of one extra (launch-by-launch) step -> {kernel: [ms]}, {kernel: [bytes, flops]}"""
+    eng = net.fused_engine()
+    eng.timeline = []
+    step_resident()
+    torch.cuda.synchronize()
+    per_kernel, per_work = {}, {}
+    for name, s, e, work in eng.timeline:
+        per_kernel.setdefault(name, []).append(s.elapsed_time(e))
+        w = per_work.setdefault(name, [0, 0])
+        w[0] += work[0]
+        w[1] += work[1]
+    eng.timeline = None
+    return per_kernel, per_work
+
+
+def rooflines_from(per_kernel, per_work):
+    hbm_peak, tf_peak, peak_kind = peaks()
+    shares = sorted(((sum(v), k, len(v)) for k, v in per_kernel.items()), reverse=True)
+    tot = sum(s for s, _, _ in shares)
+    mlp_kernels = {k for k in per_kernel if any(t in k for t in ("set_conv", "pointwise_mlp", "cost_volume"))}
+    traffic_tab, traffic_src = ncu_traffic()
+
+    def traffic_of(name):
+        fam = "pwclo_knn" if name.startswith("pwclo_knn") else name.replace("_prefix", "")
+        t = traffic_tab.get(fam)
+        return (t["dram_bytes_per_launch"], traffic_src) if t else (None, None)
+
+    def roof_of(name):
+        """achieved = algorithmic bytes (or MLP flops) of all launches of this kernel / their summed duration"""
+        ms = sum(per_kernel[name])
+        by, fl = per_work[name]
+        traffic, tsrc = traffic_of(name)
+        if name in mlp_kernels:
+            ach = fl / (ms * 1e-3) / 1e12
+            return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": ach / tf_peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)",
+                    "traffic_source": tsrc, "peak_kind": peak_kind + " (cuBLAS bf16 sustained)",
+                    "ms_per_step": ms, "launches_per_step": len(per_kernel[name]),
+                    "note": "fp32-accurate split product (tf32 + 2 bf16 correction MMAs: 8 tcgen05.mma per 32 inputs); "
+                            "flops counted once; the kernels are bound by TMEM operand/accumulator reads, see DESIGN.md"}
+        ach = by / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)", "traffic_source": tsrc,
+                "algorithmic_bytes_per_launch": by / max(1, len(per_kernel[name])),
+                "peak_kind": peak_kind, "ms_per_step": ms, "launches_per_step": len(per_kernel[name]),
+                "note": "algorithmic bytes of SURVEY 8d; this kernel is latency/ALU bound, not HBM bound"}
+
+    return ([roof_of(k) for _, k, _ in shares[:6]],
+            [{"kernel": k, "ms": round(s, 4), "launches": n, "share": round(s / tot, 4)} for s, k, n in shares])
+
+
+# ------------------------------------------------------------------------------------------------- extras
+def extra_latency(ctx, net, h1, h2):
+    """N = 1: GPU time of ONE forward at 1 / 8 / 64 pairs, replayed CUDA graph against launch-by-launch"""
+    dev, out = ctx.dev, []
+    eng = net.fused_engine()
+    for B in (1, 8, 64):
+        if B > h1.shape[0]:
+            continue
+        a, b = torch.from_numpy(h1[:B]).to(dev), torch.from_numpy(h2[:B]).to(dev)
+
+        def graphed():
+            with torch.no_grad():
+                return net(a, None, b, None)[0]
+
+        def eager():
+            with torch.no_grad():
+                return eng.forward(a, b)[0]
+
+        row = {"pairs": B}
+        for name, fn in (("graph_ms", graphed), ("eager_ms", eager)):
+            for _ in range(3):
+                fn()
+            ms, _ = ctx.timed(fn, 10)
+            row[name] = ms / 10
+        row["graphed"] = eng._graphs.get((B, h1.shape[2])) not in (None, False)
+        out.append(row)
+    return out
+
+
+def extra_config2(ctx):
+    """BASELINE config 2: the PointNet++ op suite alone at batch 8 clouds of 8192 points -- FPS 8192->2048->1024->256,
+    kNN k = 32 / 32 / 16, gather (C = 3), group (xyz + features) -- algorithmic bytes of SURVEY 8d over the measured time,
+    plus kNN point-pair evaluations per second (the kernel is ALU-bound: that is its meaningful rate)."""
+    from pwclonet_pylidarslam_b200 import _ext
+    dev = ctx.dev
+    hbm_peak, _, _ = peaks()
+    g = torch.Generator(device=dev).manual_seed(0)
+    res = []
+
+    def t(fn):
+        for _ in range(2):
+            fn()
+        ms, _ = ctx.timed(fn, 5)
+        return ms / 5
+
+    for B in (8, 128):
+        cur = (torch.randn(B, 8192, 3, device=dev, generator=g) * torch.tensor([20., 1., 20.], device=dev)).contiguous()
+        for (N, M, K, C) in ((8192, 2048, 32, 3), (2048, 1024, 32, 16), (1024, 256, 16, 32)):
+            idx = _ext.furthest_point_sampling(cur, M)
+            ms = t(lambda: _ext.furthest_point_sampling(cur, M))
+            alg = 4 * B * (3 * N + M)
+            res.append(dict(op="fps", B=B, N=N, M=M, ms=ms, gbs=alg / ms / 1e6, frac_hbm=alg / ms / 1e6 / hbm_peak,
+                            us_per_round=ms * 1e3 / (M - 1)))
+            flipped = cur.transpose(1, 2).contiguous()
+            new = _ext.gather_points(flipped, idx)
+            ms = t(lambda: _ext.gather_points(flipped, idx))
+            alg = 4 * B * (M + 3 * M + 3 * N)
+            res.append(dict(op="gather", B=B, N=N, M=M, ms=ms, gbs=alg / ms / 1e6, frac_hbm=alg / ms / 1e6 / hbm_peak))
+            new_xyz = new.transpose(1, 2).contiguous()
+            nidx = _ext.knn(cur, new_xyz, K)
+            ms = t(lambda: _ext.knn(cur, new_xyz, K))
+            alg = 4 * B * (3 * M + 3 * N + M * K)
+            res.append(dict(op="knn", B=B, N=N, S=M, K=K, ms=ms, gbs=alg / ms / 1e6, frac_hbm=alg / ms / 1e6 / hbm_peak,
+                            gpairs_per_s=B * M * N / ms / 1e6))
+            for Cg in sorted({3, C}):
+                feats = torch.randn(B, Cg, N, device=dev, generator=g)
+                ms = t(lambda: _ext.group_points(feats, nidx))
+                alg = 4 * B * (M * K + Cg * M * K + Cg * N)
+                res.append(dict(op="group", B=B, C=Cg, N=N, S=M, K=K, ms=ms, gbs=alg / ms / 1e6,
+                                frac_hbm=alg / ms / 1e6 / hbm_peak))
+            cur = new_xyz
+    # a launch large enough to be HBM-bound: C = 64 rows of N = 2048 grouped into S = 2048, K = 32 for 64 clouds
+    B, C, N, S, K = 64, 64, 2048, 2048, 32
+    feats = torch.randn(B, C, N, device=dev, generator=g)
+    idx = torch.randint(0, N, (B, S, K), device=dev, dtype=torch.int32, generator=g)
+    ms = t(lambda: _ext.group_points(feats, idx))
+    alg = 4 * B * (S * K + C * S * K + C * N)
+    res.append(dict(op="group_big", B=B, C=C, N=N, S=S, K=K, ms=ms, gbs=alg / ms / 1e6, frac_hbm=alg / ms / 1e6 / hbm_peak))
+    for r in res:
+        for k, v in list(r.items()):
+            if isinstance(v, float):
+                r[k] = round(v, 5)
+    return {"config": "BASELINE config 2: op suite, batch 8 clouds x 8192 points (B = 128: the batch of the full forward)",
+            "hbm_peak_gbs": hbm_peak, "ops": res}
+
+
+def extra_config3(ctx, net, h1, h2, pairs=16):
+    """BASELINE config 3: the four attentive cost volumes and the six set-upconvs inside a real forward of 16 pairs"""
+    dev = ctx.dev
+    _, tf_peak, _ = peaks()
+    eng = net.fused_engine()
+    a, b = torch.from_numpy(h1[:pairs]).to(dev), torch.from_numpy(h2[:pairs]).to(dev)
+    eng.verbose_timeline = True
+    runs = []
+    with torch.no_grad():
+        for _ in range(2):
+            eng.forward(a, b)
+        for _ in range(5):
+            ctx.flush.zero_()
+            eng.timeline = []
+            eng.forward(a, b)
+            torch.cuda.synchronize()
+            runs.append([(n, s.elapsed_time(e), w) for n, s, e, w in eng.timeline])
+            eng.timeline = None
+    eng.verbose_timeline = False
+    names = [n for n, _, _ in runs[0]]
+    med = [float(np.median([r[i][1] for r in runs])) for i in range(len(names))]
+    work = [runs[0][i][2] for i in range(len(names))]
+    tot_ms = tot_fl = 0.0
+    rows = []
+    for i, n in enumerate(names):
+        post = n.startswith("pwclo_pointwise_mlp") and i > 0 and "setupconv" in names[i - 1]
+        if not (n.startswith("pwclo_cost_volume") or "setupconv" in n or post):
+            continue
+        rows.append({"kernel": n + ("[post_mlp]" if post else ""), "ms": round(med[i], 4),
+                     "tflops": round(work[i][1] / (med[i] * 1e-3) / 1e12, 1)})
+        tot_ms += med[i]
+        tot_fl += work[i][1]
+    return {"config": f"BASELINE config 3: attentive cost volume + set_upconv at all 4 pyramid levels, batch {pairs} frame pairs",
+            "ms_total": tot_ms, "gflop_total": tot_fl / 1e9, "gflop_per_pair": tot_fl / 1e9 / pairs,
+            "tflops": tot_fl / (tot_ms * 1e-3) / 1e12, "frac_of_bf16_peak": tot_fl / (tot_ms * 1e-3) / 1e12 / tf_peak,
+            "forward_ms": float(sum(med)), "kernels": rows}
+
+
+def measure_train(ctx, args, steps, warmup):
+    """BASELINE config 5: training step = zero_grad, forward (train-mode BN, dropout), loss, backward, ONE
+    NCCL all-reduce of the flat gradient arena, one-launch Adam; `--train-pairs-per-gpu` pairs of `--train-points`
+    points per GPU (weak scaling by definition: the batch per GPU is the configuration).  Every rank calls it."""
     from pwclonet_pylidarslam_b200 import training as T
-    _lib.lib()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    NP, P = args.train_points, args.train_pairs_per_gpu
+    torch.backends.cudnn.allow_tf32 = False          # "dtype": "f32" must mean fp32 for the library GEMMs too
+    torch.backends.cuda.matmul.allow_tf32 = False
+    h1, h2 = make_inputs(50 + rank, P, P, n_points=NP)
     torch.manual_seed(0)
-    tr = T.PWCLONetTrainer(T.PWCLONetTrainerConfig(num_points=N_POINTS, device=str(dev), batch_size=P))
+    tr = T.PWCLONetTrainer(T.PWCLONetTrainerConfig(num_points=NP, device=str(dev), batch_size=P))
     rng = np.random.default_rng(7 + rank)
     q = rng.standard_normal((P, 4)).astype(np.float32) * 0.02 + np.array([1, 0, 0, 0], np.float32)
     q /= np.linalg.norm(q, axis=-1, keepdims=True)
@@ -229,20 +528,8 @@ def run_train(args, world, rank, local):
            torch.from_numpy(np.ascontiguousarray(h2.transpose(0, 2, 1))).pin_memory(),
            torch.from_numpy(q).pin_memory(), torch.from_numpy(t).pin_memory()]
     res = [b.to(dev) for b in pin]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     graphed = not args.no_graph
     graph_note = "whole step (zero_grad, forward, loss, backward, all-reduce, Adam) replayed as one CUDA graph"
-    if graphed and world > 1:
-        # measured on 2 B200: capturing the NCCL all-reduce inside the step graph hung (round-1 run r2f, killed by the
-        # 900 s limit); the data-parallel step therefore runs eagerly until that is understood
-        graphed, graph_note = False, "eager step (graph capture with the NCCL all-reduce inside is disabled for world > 1)"
     if graphed:
         try:
             tr.capture(res)
@@ -252,6 +539,11 @@ def run_train(args, world, rank, local):
             torch.cuda.synchronize()
     else:
         graph_note = "eager step (one launch per op, host-bound)"
+    if world > 1:       # all ranks must replay the same thing: a rank whose capture failed would deadlock the others
+        ok = ctx.max_over_ranks([0.0 if graphed else 1.0])[0] == 0.0
+        if graphed and not ok:
+            graphed, graph_note = False, "CUDA-graph capture failed on another rank; eager step"
+            tr.drop_graph()
     step_fn = tr.train_step_graphed if graphed else tr.train_step
 
     def step_resident():
@@ -260,32 +552,20 @@ def run_train(args, world, rank, local):
     def step_e2e():
         return step_fn(pin if graphed else [b.to(dev, non_blocking=True) for b in pin])[0].cpu()
 
-    def timed(fn, steps):
-        evs = []
-        for _ in range(steps):
-            flush.zero_()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            out = fn()
-            e.record()
-            evs.append((s, e))
-        torch.cuda.synchronize()
-        return sum(s.elapsed_time(e) for s, e in evs), out
-
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, warmup)):
         step_resident()
-    sampler = ClockSampler(local)
-    barrier()
+    sampler = ClockSampler(ctx.local)
+    ctx.barrier()
     sampler.start()
-    ms_total, loss = timed(step_resident, args.steps)
-    barrier()
+    ms_total, loss = ctx.timed(step_resident, steps)
+    ctx.barrier()
     sampler.stop_flag = True
     step_e2e()
-    barrier()
-    ms_e2e, _ = timed(step_e2e, args.steps)
-    barrier()
-    # the collective and the optimiser alone (CUDA events on the launching stream)
-    def alone(fn, n=20):
+    ctx.barrier()
+    ms_e2e, _ = ctx.timed(step_e2e, steps)
+    ctx.barrier()
+
+    def alone(fn, n=20):    # the collective and the optimiser alone (CUDA events on the launching stream)
         fn()
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -297,37 +577,69 @@ def run_train(args, world, rank, local):
         return s.elapsed_time(e) / n
     ms_ar = alone(lambda: T.all_reduce_gradients(tr.arena))
     ms_adam = alone(lambda: tr._optimizer.step(1.0))
-    tt = torch.tensor([ms_total, ms_e2e, ms_ar, ms_adam], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_ar, ms_adam = [float(v) for v in tt]
-    if rank == 0:
+    ms_total, ms_e2e, ms_ar, ms_adam = ctx.max_over_ranks([ms_total, ms_e2e, ms_ar, ms_adam])
+    loss = float(loss)
+    out = {"metric": f"PWCLO-Net training frame-pairs/s ({NP} pts, fwd+bwd+allreduce+Adam)",
+           "value": world * P * steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+           "ms_per_step": ms_total / steps, "scaling": "weak", "dtype": "f32 (cudnn / matmul TF32 disabled)",
+           "pairs_per_gpu": P, "points": NP, "execution": graph_note, "graphed": graphed,
+           "parallelism": f"data parallel x{world}, one NCCL all-reduce of {tr.arena.numel} fp32 per step",
+           "e2e": {"value": world * P * steps / (ms_e2e * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": int(sum(b.numel() * 4 for b in pin)), "d2h_bytes_per_step": 4,
+                   "ms_per_step": ms_e2e / steps},
+           "allreduce_ms": ms_ar, "allreduce_bytes": tr.arena.numel * 4, "adam_ms": ms_adam, "loss": loss,
+           "clocks": sampler.summary(),
+           "note": "sampling / neighbour / grouping ops, train-mode BatchNorm + ReLU, the pose warp, the loss and Adam on the "
+                   "sm_100a kernels; the 1x1 convolutions wider than 16 channels, concatenations, softmax and max-pool "
+                   "(and their backward) by torch"}
+    # teardown in the order that does not leave NCCL work referenced by a live graph (round-1 hang at exit)
+    tr.close()
+    del tr
+    return out
+
+
+def run_train(args, ctx):
+    """--mode train: config 5 as the headline line"""
+    global N_POINTS
+    N_POINTS = args.train_points
+    m = measure_train(ctx, args, args.steps, args.warmup)
+    if ctx.rank == 0:
         hbm_peak, _, peak_kind = peaks()
-        adam_bytes = tr.arena.numel * 28
-        ach = adam_bytes / (ms_adam * 1e-3) / 1e9
-        line = {"metric": f"PWCLO-Net training frame-pairs/s ({N_POINTS} pts, fwd+bwd+allreduce+Adam)",
-                "value": world * P * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        adam_bytes = m["allreduce_bytes"] * 7
+        ach = adam_bytes / (m["adam_ms"] * 1e-3) / 1e9
+        line = {"metric": m["metric"], "value": m["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": m["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"BASELINE config 5: training forward+backward, {P} frame pairs per GPU x {N_POINTS} points, "
-                                       "train-mode BatchNorm + dropout, one all-reduce of the flat gradient arena, Adam",
-                           "pairs_per_gpu": P, "points": N_POINTS, "l2": "flushed between timed steps (256 MB write)",
-                           "parallelism": f"data parallel x{world}, one NCCL all-reduce of {tr.arena.numel} fp32 per step",
-                           "execution": graph_note,
-                           "note": "sampling / neighbour / grouping ops and the loss on the sm_100a kernels; 1x1 convs, BN and "
-                                   "their backward by torch (fused-layer backward is not built)"},
-                "e2e": {"value": world * P * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-                        "h2d_bytes_per_step": int(sum(b.numel() * 4 for b in pin)), "d2h_bytes_per_step": 4,
-                        "ms_per_step": ms_e2e / args.steps},
-                "allreduce_ms": ms_ar, "allreduce_bytes": tr.arena.numel * 4, "adam_ms": ms_adam,
-                "loss": float(loss), "clocks": sampler.summary(),
+                "config": {"workload": f"BASELINE config 5: training forward+backward, {m['pairs_per_gpu']} frame pairs per GPU x "
+                                       f"{m['points']} points, train-mode BatchNorm + dropout, one all-reduce of the flat "
+                                       "gradient arena, Adam",
+                           "pairs_per_gpu": m["pairs_per_gpu"], "points": m["points"],
+                           "l2": "flushed between timed steps (256 MB write)", "parallelism": m["parallelism"],
+                           "execution": m["execution"], "tf32": "disabled (cudnn + matmul)", "note": m["note"]},
+                "e2e": m["e2e"], "allreduce_ms": m["allreduce_ms"], "allreduce_bytes": m["allreduce_bytes"],
+                "adam_ms": m["adam_ms"], "loss": m["loss"], "clocks": m["clocks"],
                 "roofline": {"bound": "hbm", "kernel": "pwclo_adam_step", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                              "frac": ach / hbm_peak, "traffic": None, "peak_kind": peak_kind,
                              "note": "the one training kernel that is purely HBM streaming (28 B per parameter); 3.1 MB "
                                      "arena stays in L2 between steps, so this is an L2-resident figure"}}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def finish(ctx):
+    """leave without hanging: a clean process-group teardown, bounded by a timer"""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if ctx.world > 1:
+        killer = threading.Timer(30.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
+        try:
+            torch.cuda.synchronize()
+            ctx.dist.barrier()
+            ctx.dist.destroy_process_group()
+        except Exception:
+            pass
+        killer.cancel()
 
 
 def main():
@@ -347,178 +659,121 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+
+    from pwclonet_pylidarslam_b200 import _lib
+    from pwclonet_pylidarslam_b200 import sharding
+    _lib.lib()   # fail loudly right away if the CUDA library is missing
     if args.mode == "train":
-        run_train(args, world, rank, local)
+        ctx = Ctx(world, rank, local)
+        run_train(args, ctx)
+        finish(ctx)
         return
 
-    P = args.pairs_per_gpu
-    h1, h2 = make_inputs(rank, P, args.distinct)      # host-side ray casting (forks workers) before CUDA comes up
-    import torch.distributed as dist
-    from pwclonet_pylidarslam_b200 import _lib
-    from pwclonet_pylidarslam_b200.pwclonet import PWCLONet
-    _lib.lib()   # fail loudly right away if the CUDA library is missing
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
+    # ---- inputs: every rank builds its slice of the same global batch (host-side ray casting forks workers: before CUDA)
+    T = args.total_pairs
+    strong = args.scaling == "strong"
+    lo, hi = sharding.shard_range(T, rank, world) if strong else (0, T)
+    extras = set() if args.extras == "none" else {e for e in args.extras.split(",") if e}
+    need_all = (not strong) or ("weak" in extras and world > 1) or world == 1
+    g1, g2 = make_inputs(0, T, args.distinct, lo=0 if need_all else lo, hi=T if need_all else hi)
+    h1, h2 = (g1[lo:hi], g2[lo:hi]) if need_all else (g1, g2)
+    ctx = Ctx(world, rank, local)
     weights = make_weights()
-    net = PWCLONet({"device": str(dev)})
-    net.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
-    net = net.to(dev).eval()
-    pin1, pin2 = torch.from_numpy(h1).pin_memory(), torch.from_numpy(h2).pin_memory()
-    d1, d2 = pin1.to(dev), pin2.to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    eng = net.fused_engine()
+    net = build_net(ctx.dev, weights)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step_resident():
-        with torch.no_grad():
-            return net(d1, None, d2, None)[0]
-
-    def step_e2e():
-        with torch.no_grad():
-            a = pin1.to(dev, non_blocking=True)
-            b = pin2.to(dev, non_blocking=True)
-            return net(a, None, b, None)[0].cpu()
-
-    def timed(fn, steps):
-        evs = []
-        for _ in range(steps):
-            flush.zero_()                       # L2 flush between timed iterations (outside the timed events)
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            out = fn()
-            e.record()
-            evs.append((s, e))
-        torch.cuda.synchronize()
-        return sum(s.elapsed_time(e) for s, e in evs), out
-
-    for _ in range(max(3, args.warmup)):
-        step_resident()
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    launches0 = eng.launches
-    ms_total, pose = timed(step_resident, args.steps)
-    launches = eng.launches - launches0
-    barrier()
-    sampler.stop_flag = True
-    # e2e: the streaming public API (sharding.PosePipeline): every step's two clouds are copied from pinned host
-    # memory and its pose is read back to the host inside the timed region; the copy of step i+1 overlaps the
-    # forward of step i.  The L2 flush between steps is inside the timed region here (it cannot be bracketed out
-    # of an overlapped pipeline), so this number is slightly conservative.
-    from pwclonet_pylidarslam_b200.sharding import PosePipeline
-    pipe = PosePipeline(net, P, N_POINTS)
-
-    def host_batches(k):
-        for _ in range(k):
-            flush.zero_()
-            yield pin1, pin2
-
-    for _ in pipe.run(host_batches(3)):
-        pass
-    barrier()
-    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s_ev.record()
-    for pose_h in pipe.run(host_batches(args.steps)):
-        pass
-    e_ev.record()
-    torch.cuda.synchronize()
-    ms_e2e = s_ev.elapsed_time(e_ev)
-    barrier()
-    step_e2e()
-    ms_e2e_serial, _ = timed(step_e2e, args.steps)      # copy -> forward -> read back, nothing overlapped
-    barrier()
-
-    # per-kernel timeline (CUDA events around every launch of one extra step) -> dominant kernel
-    eng.timeline = []
-    step_resident()
-    torch.cuda.synchronize()
-    per_kernel, per_work = {}, {}
-    for name, s, e, work in eng.timeline:
-        per_kernel.setdefault(name, []).append(s.elapsed_time(e))
-        w = per_work.setdefault(name, [0, 0])
-        w[0] += work[0]
-        w[1] += work[1]
-    eng.timeline = None
-    step_ms = ms_total / args.steps
-
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = float(t[0]), float(t[1])
-    value = world * P * args.steps / (ms_total * 1e-3)
-    e2e = world * P * args.steps / (ms_e2e * 1e-3)
-
+    pairs_total = T if strong else T * world
+    m = measure_forward(ctx, net, h1, h2, args.steps, args.warmup, pairs_total)
+    per_kernel, per_work = kernel_timeline(net, m["step_resident"])
+    line = None
     if rank == 0:
-        hbm_peak, tf_peak, peak_kind = peaks()
-        shares = sorted(((sum(v), k, len(v)) for k, v in per_kernel.items()), reverse=True)
-        tot = sum(s for s, _, _ in shares)
-        top_ms, top_name, top_n = shares[0]
-        mlp_kernels = {k for k in per_kernel if any(t in k for t in ("set_conv", "pointwise_mlp", "cost_volume"))}
-
-        traffic_tab, traffic_src = ncu_traffic()
-
-        def traffic_of(name):
-            fam = "pwclo_knn" if name.startswith("pwclo_knn") else name
-            t = traffic_tab.get(fam)
-            return (t["dram_bytes_per_launch"], traffic_src) if t else (None, None)
-
-        def roof_of(name):
-            """achieved = algorithmic bytes (or MLP flops) of all launches of this kernel / their summed duration"""
-            ms = sum(per_kernel[name])
-            by, fl = per_work[name]
-            traffic, tsrc = traffic_of(name)
-            if name in mlp_kernels:
-                ach = fl / (ms * 1e-3) / 1e12
-                return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
-                        "frac": ach / tf_peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)",
-                        "traffic_source": tsrc, "peak_kind": peak_kind + " (cuBLAS bf16 sustained)",
-                        "ms_per_step": ms, "launches_per_step": len(per_kernel[name]),
-                        "note": "fp32-accurate split product (tf32 + 2 bf16 correction MMAs: 8 tcgen05.mma per 32 inputs); "
-                                "flops counted once; the kernels are bound by TMEM operand/accumulator reads, see DESIGN.md"}
-            ach = by / (ms * 1e-3) / 1e9
-            return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)", "traffic_source": tsrc,
-                    "algorithmic_bytes_per_launch": by / max(1, len(per_kernel[name])),
-                    "peak_kind": peak_kind, "ms_per_step": ms, "launches_per_step": len(per_kernel[name]),
-                    "note": "algorithmic bytes of SURVEY 8d; this kernel is latency/ALU bound, not HBM bound"}
-
-        roof = roof_of(top_name)
-        rooflines = [roof_of(k) for _, k, _ in shares[:6]]
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"PWCLO-Net full 4-level inference forward, {P} frame pairs per GPU x {N_POINTS} points "
-                                       "(BASELINE config: batch 64 frame pairs), synthetic KITTI-64-beam clouds, random-init "
-                                       "weights with non-trivial BN statistics",
-                           "pairs_per_gpu": P, "points": N_POINTS, "l2": "flushed between timed steps (256 MB write)",
-                           "parallelism": f"frame-pair sharding x{world}, no collective"},
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pin1.numel() * 4 * 2),
-                        "d2h_bytes_per_step": int(pose.numel() * 4), "ms_per_step": ms_e2e / args.steps,
-                        "api": "sharding.PosePipeline (copy of step i+1 overlaps the forward of step i; L2 flush inside "
-                               "the timed region)",
-                        "serial_value": world * P * args.steps / (ms_e2e_serial * 1e-3),
-                        "serial_note": "net(x1.to(dev), None, x2.to(dev), None)[0].cpu() per step, rank 0"},
-                "gpu_launches": int(launches),
-                "clocks": sampler.summary(),
-                "roofline": roof,
+        rooflines, shares = rooflines_from(per_kernel, per_work)
+        per_gpu = hi - lo
+        line = {"metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": m["ms_total"] / args.steps, "higher_is_better": True,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"BASELINE config 4: PWCLO-Net full 4-level pose warp-refinement inference forward, batch "
+                                       f"{pairs_total} frame pairs x {N_POINTS} points "
+                                       + (f"sharded over {world} GPU(s) ({per_gpu} pairs per GPU)" if strong
+                                          else f"({T} pairs on every one of {world} GPUs)")
+                                       + ", synthetic KITTI-64-beam clouds, random-init weights with non-trivial BN statistics",
+                           "total_pairs": pairs_total, "pairs_per_gpu": per_gpu, "points": N_POINTS,
+                           "l2": "flushed between timed steps (256 MB write)",
+                           "execution": "whole forward replayed as one CUDA graph per step",
+                           "parallelism": f"frame-pair sharding x{world}, no data-path collective"},
+                "e2e": {"value": m["e2e"], "unit": UNIT, "h2d_bytes_per_step": m["h2d"] * (world if strong else world),
+                        "d2h_bytes_per_step": m["d2h"] * world, "ms_per_step": m["ms_e2e"] / args.steps,
+                        "api": "sharding.PosePipeline on every rank's shard (copy of step i+1 overlaps the forward of step i; "
+                               "L2 flush inside the timed region)",
+                        "serial_value": m["e2e_serial"],
+                        "serial_note": "net(x1.to(dev), None, x2.to(dev), None)[0].cpu() per step"},
+                "gpu_launches": m["launches"],
+                "clocks": m["clocks"],
+                "roofline": rooflines[0],
                 "rooflines": rooflines,
-                "kernel_shares": [{"kernel": k, "ms": round(s, 4), "launches": n, "share": round(s / tot, 4)} for s, k, n in shares],
-                "step_ms_rank0": step_ms}
-        if world == 1 and not args.no_cpu_baseline:
-            v, ms, sample = cpu_reference(weights, 5, 1)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": sample, "ms_per_pair": ms, "host": host_info()}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+                "kernel_shares": shares,
+                "kernel_shares_note": f"rank 0, one launch-by-launch forward of its {per_gpu} pairs (CUDA events around every launch)",
+                "step_ms_rank0": m["ms_total_rank"] / args.steps,
+                "forward_gflop_per_pair": FLOP_PER_PAIR / 1e9,
+                "forward_tflops": FLOP_PER_PAIR * m["value"] / 1e12}
+
+    # ---- extra keys; if one of them stalls, the line goes out without it
+    state = {"printed": False}
+    lock = threading.Lock()
+
+    def emit(note=None):
+        with lock:
+            if state["printed"]:
+                return
+            state["printed"] = True
+            if rank == 0:
+                if note:
+                    line["extras_note"] = note
+                print(json.dumps(line), flush=True)
+
+    def bail():
+        emit(f"extra keys not finished within {args.extras_timeout:.0f} s were dropped")
+        sys.stdout.flush()
+        os._exit(0)
+
+    dog = threading.Timer(args.extras_timeout, bail)
+    dog.daemon = True
+    dog.start()
+
+    def put(key, value):
+        if rank == 0:
+            with lock:
+                line[key] = value
+
+    def guarded(key, fn):
+        try:
+            put(key, fn())
+        except Exception as e:           # an extra key must never cost the headline
+            put(key, {"error": f"{type(e).__name__}: {e}"})
+            torch.cuda.synchronize()
+
+    if "weak" in extras and world > 1 and strong:
+        def weak():
+            mw = measure_forward(ctx, net, g1, g2, max(3, args.steps // 2), 3, T * world)
+            return {"value": mw["value"], "unit": UNIT, "pairs_per_gpu": T, "ms_per_step": mw["ms_total"] / max(3, args.steps // 2),
+                    "e2e": mw["e2e"], "note": f"replicas: {T} pairs on EVERY GPU (per-GPU work fixed), no collective"}
+        guarded("weak", weak)
+    if world == 1:
+        if "latency" in extras:
+            guarded("latency", lambda: extra_latency(ctx, net, g1, g2))
+        if "config3" in extras:
+            guarded("config3", lambda: extra_config3(ctx, net, g1, g2))
+        if "config2" in extras:
+            guarded("config2", lambda: extra_config2(ctx))
+    del net
+    if "train" in extras:
+        guarded("train", lambda: measure_train(ctx, args, max(3, min(args.steps, 10)), 3))
+    if world == 1 and not args.no_cpu_baseline and rank == 0:
+        v, ms, sample = cpu_reference(weights, 5, 1)
+        put("cpu_baseline", {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                             "sample": sample, "ms_per_pair": ms, "host": host_info()})
+    dog.cancel()
+    emit()
+    finish(ctx)
 
 
 if __name__ == "__main__":

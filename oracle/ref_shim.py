@@ -1,4 +1,4 @@
-"""oracle/ref_shim.py -- TEST INFRASTRUCTURE ONLY; works only where /root/reference is mounted.
+"""oracle/ref_shim.py -- TEST INFRASTRUCTURE ONLY; needs /root/reference or its staged python files (baseline/_ref).
 
 Imports the UNMODIFIED reference PWCLO-Net (slam/models/PWCLONet/pwclo_net.py:32-207) on CPU by
 injecting the import stubs listed in SURVEY.md section 9.7 (omegaconf, slam.common.utils,
@@ -11,7 +11,17 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("PWCLO_REFERENCE_ROOT", "/root/reference")
+def _find_root():
+    """/root/reference where it is mounted (this container); on the GPU box the unmodified hot-path python files staged
+    by oracle/stage_reference.py into the git-ignored baseline/_ref/"""
+    if os.environ.get("PWCLO_REFERENCE_ROOT"):
+        return os.environ["PWCLO_REFERENCE_ROOT"]
+    if os.path.isdir("/root/reference/slam/models/PWCLONet"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+REF_ROOT = _find_root()
 P2_LIB = os.path.join(REF_ROOT, "slam/models/Pointnet2_PyTorch/pointnet2_ops_lib")
 
 

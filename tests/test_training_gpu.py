@@ -281,3 +281,20 @@ def test_skinny_conv1x1_matches_torch(cuda, B, CI, CO, S, K, need_dx):
     for name, a, r in zip(("y", "dw", "dx"), got, want):
         err = float((a - r).abs().max())
         assert err <= 1e-5 * float(r.abs().max()) + 1e-7, (name, err, float(r.abs().max()))
+
+
+def test_ddp_graphed_step_equals_eager_step(cuda):
+    """2 GPUs: PWCLONetTrainer.capture with the NCCL all-reduce inside the graph replays the eager data-parallel step
+    (same losses, ranks stay identical) and the processes exit cleanly (trainer.close() before destroy_process_group).
+    Runs tools/ddp_graph_probe.py under torchrun; skipped on a single-GPU box."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29561", os.path.join(root, "tools", "ddp_graph_probe.py")],
+                       capture_output=True, text=True, timeout=240, cwd=root)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "rank 0: OK" in out and "rank 1: OK" in out, out[-3000:]

@@ -1,15 +1,21 @@
-"""2-rank probe for tools/try_ddp_graph.sh: capture the data-parallel training step (PWCLO_GRAPH_DDP=1) on a small problem
-and compare three replays with the eager step of an identically initialised trainer."""
+"""2-rank check of the data-parallel training step replayed as one CUDA graph (NCCL all-reduce captured inside):
+graphed losses == eager losses of an identically initialised trainer, then a clean teardown (trainer.close()).
+Launched by tests/test_training_gpu.py::test_ddp_graphed_step_equals_eager_step and tools/try_ddp_graph.sh under
+torchrun; prints `rank r: OK` per rank.  Dropout is switched off (eager and replay draw different masks)."""
 import os
 import sys
+import threading
 
 import numpy as np
 import torch
 import torch.distributed as dist
+import torch.nn.functional as F_
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pwclonet_pylidarslam_b200 import synthetic as syn, training as T  # noqa: E402
 
+F_.dropout = lambda x, p=0.5, training=True, inplace=False: x
+threading.Timer(float(os.environ.get("PROBE_LIMIT_S", "140")), lambda: os._exit(3)).start()   # never hang a GPU box
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -17,12 +23,30 @@ dist.init_process_group("nccl", device_id=dev)
 x1, x2, gt = syn.make_batch(900 + 10 * local, 2, 4096)
 batch = [torch.from_numpy(np.ascontiguousarray(x1.transpose(0, 2, 1))).to(dev), torch.from_numpy(np.ascontiguousarray(x2.transpose(0, 2, 1))).to(dev),
          torch.from_numpy(gt[:, 3:]).to(dev), torch.from_numpy(gt[:, :3]).to(dev)]
+batch2 = [b.flip(0).contiguous() for b in batch]
+cfg = T.PWCLONetTrainerConfig(num_points=4096, device=str(dev))
 torch.manual_seed(0)
-tr = T.PWCLONetTrainer(T.PWCLONetTrainerConfig(num_points=4096, device=str(dev)))
-print(f"rank {local}: eager step", float(tr.train_step(batch)[0]), flush=True)
-tr.capture(batch, warmup=1)
-for i in range(3):
-    print(f"rank {local}: replay {i}", float(tr.train_step_graphed(batch)[0]), flush=True)
-dist.barrier()
+a = T.PWCLONetTrainer(cfg)
+b = T.PWCLONetTrainer(cfg)
+b.prediction_module_.load_state_dict(a.prediction_module_.state_dict())
+eager = [float(a.train_step(batch)[0]) for _ in range(2)]
+b.capture(batch, warmup=1)              # b: 1 warm-up step + 1 replay on `batch` = the same two steps as a
+b.prediction_module_.load_state_dict(a.prediction_module_.state_dict())
+b.loss_module_.load_state_dict(a.loss_module_.state_dict())
+b._optimizer.load_state_dict(a._optimizer.state_dict())
+graphed = []
+for i in range(4):
+    bt = batch if i % 2 == 0 else batch2
+    eager.append(float(a.train_step(bt)[0]))
+    graphed.append(float(b.train_step_graphed(bt)[0]))
+print(f"rank {local}: eager {eager[2:]} graphed {graphed}", flush=True)
+np.testing.assert_allclose(graphed, eager[2:], rtol=1e-3)
+# both ranks hold the same parameters after data-parallel steps
+p = b.arena.param.clone()
+dist.all_reduce(p, op=dist.ReduceOp.MAX)
+assert torch.equal(p, b.arena.param), "ranks diverged"
+b.close()
+a.close()
 dist.destroy_process_group()
-print(f"rank {local}: done", flush=True)
+print(f"rank {local}: OK", flush=True)
+os._exit(0)
