@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="train: eager step instead of the captured CUDA graph")
     ap.add_argument("--train-points", type=int, default=16384)
     ap.add_argument("--train-pairs-per-gpu", type=int, default=8)
+    ap.add_argument("--train-strict-fp32", action="store_true", help="train: cudnn / matmul TF32 off for the library GEMMs")
     return ap.parse_args()
 
 
@@ -508,15 +509,20 @@ def extra_config3(ctx, net, h1, h2, pairs=16):
             "forward_ms": float(sum(med)), "kernels": rows}
 
 
-def measure_train(ctx, args, steps, warmup):
+def measure_train(ctx, args, steps, warmup, strict_fp32=False):
     """BASELINE config 5: training step = zero_grad, forward (train-mode BN, dropout), loss, backward, ONE
     NCCL all-reduce of the flat gradient arena, one-launch Adam; `--train-pairs-per-gpu` pairs of `--train-points`
     points per GPU (weak scaling by definition: the batch per GPU is the configuration).  Every rank calls it."""
     from pwclonet_pylidarslam_b200 import training as T
     world, rank, dev = ctx.world, ctx.rank, ctx.dev
     NP, P = args.train_points, args.train_pairs_per_gpu
-    torch.backends.cudnn.allow_tf32 = False          # "dtype": "f32" must mean fp32 for the library GEMMs too
+    # The 1x1 convolutions that still run in torch follow torch's defaults, exactly as they do for a user of the reference
+    # (cudnn.allow_tf32 = True: cuDNN may use TF32 tensor cores; matmul fp32).  strict_fp32 pins both off.
+    torch.backends.cudnn.allow_tf32 = not strict_fp32
     torch.backends.cuda.matmul.allow_tf32 = False
+    tf32_note = ("disabled (cudnn + matmul): every library GEMM in fp32" if strict_fp32 else
+                 "torch defaults, as in the reference's environment: cudnn.allow_tf32=True (library 1x1 convolutions may use "
+                 "TF32 tensor cores), matmul fp32; everything on this repository's kernels is fp32")
     h1, h2 = make_inputs(50 + rank, P, P, n_points=NP)
     torch.manual_seed(0)
     tr = T.PWCLONetTrainer(T.PWCLONetTrainerConfig(num_points=NP, device=str(dev), batch_size=P))
@@ -581,7 +587,7 @@ def measure_train(ctx, args, steps, warmup):
     loss = float(loss)
     out = {"metric": f"PWCLO-Net training frame-pairs/s ({NP} pts, fwd+bwd+allreduce+Adam)",
            "value": world * P * steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
-           "ms_per_step": ms_total / steps, "scaling": "weak", "dtype": "f32 (cudnn / matmul TF32 disabled)",
+           "ms_per_step": ms_total / steps, "scaling": "weak", "dtype": "f32", "tf32": tf32_note,
            "pairs_per_gpu": P, "points": NP, "execution": graph_note, "graphed": graphed,
            "parallelism": f"data parallel x{world}, one NCCL all-reduce of {tr.arena.numel} fp32 per step",
            "e2e": {"value": world * P * steps / (ms_e2e * 1e-3), "unit": UNIT,
@@ -595,6 +601,7 @@ def measure_train(ctx, args, steps, warmup):
     # teardown in the order that does not leave NCCL work referenced by a live graph (round-1 hang at exit)
     tr.close()
     del tr
+    torch.backends.cudnn.allow_tf32 = True
     return out
 
 
@@ -602,7 +609,7 @@ def run_train(args, ctx):
     """--mode train: config 5 as the headline line"""
     global N_POINTS
     N_POINTS = args.train_points
-    m = measure_train(ctx, args, args.steps, args.warmup)
+    m = measure_train(ctx, args, args.steps, args.warmup, strict_fp32=args.train_strict_fp32)
     if ctx.rank == 0:
         hbm_peak, _, peak_kind = peaks()
         adam_bytes = m["allreduce_bytes"] * 7
@@ -615,7 +622,7 @@ def run_train(args, ctx):
                                        "gradient arena, Adam",
                            "pairs_per_gpu": m["pairs_per_gpu"], "points": m["points"],
                            "l2": "flushed between timed steps (256 MB write)", "parallelism": m["parallelism"],
-                           "execution": m["execution"], "tf32": "disabled (cudnn + matmul)", "note": m["note"]},
+                           "execution": m["execution"], "tf32": m["tf32"], "note": m["note"]},
                 "e2e": m["e2e"], "allreduce_ms": m["allreduce_ms"], "allreduce_bytes": m["allreduce_bytes"],
                 "adam_ms": m["adam_ms"], "loss": m["loss"], "clocks": m["clocks"],
                 "roofline": {"bound": "hbm", "kernel": "pwclo_adam_step", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
@@ -767,6 +774,11 @@ def main():
     del net
     if "train" in extras:
         guarded("train", lambda: measure_train(ctx, args, max(3, min(args.steps, 10)), 3))
+        if world == 1:
+            def strict():
+                m = measure_train(ctx, args, 5, 3, strict_fp32=True)
+                return {k: m[k] for k in ("value", "ms_per_step", "tf32", "graphed")}
+            guarded("train_strict_fp32", strict)
     if world == 1 and not args.no_cpu_baseline and rank == 0:
         v, ms, sample = cpu_reference(weights, 5, 1)
         put("cpu_baseline", {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",

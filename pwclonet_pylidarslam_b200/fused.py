@@ -185,7 +185,12 @@ class FusedPWCLONet:
         self.L = {k: A.layers(v) for k, v in self.recs.items() if isinstance(v, list)}
         self.LT = {k: A.layers(v) for k, v in self.tc_recs.items()}
         self.use_tc = os.environ.get("PWCLO_TC", "1") != "0"
-        self.fps_prefix = os.environ.get("PWCLO_FPS_PREFIX", "1") != "0"
+        # FPS prefix shortcut (pwclo_furthest_point_sampling_prefix): OFF by default.  Measured on the B200
+        # (tools/bench_fps_prefix.py, profiles/r2b_fps_prefix.json): tracking arg-max ties costs +40 % on the level-1
+        # sampling (0.89 -> 1.26 ms: the check sits on the serial round chain), ~6 % of the synthetic LiDAR clouds do see an
+        # exact fp32 tie of two running minima in 2047 rounds, and a launch lasts as long as its slowest cloud -- so with
+        # 128 clouds per launch levels 2-4 (0.39 ms) are never skipped.  It pays only for single tie-free clouds.
+        self.fps_prefix = os.environ.get("PWCLO_FPS_PREFIX", "0") == "1"
         self._sorted = {}
         self._graphs = {}        # (B, N) -> captured whole-forward CUDA graph (forward_graphed)
         self.use_graph = os.environ.get("PWCLO_INFER_GRAPH", "1") != "0"
@@ -199,8 +204,13 @@ class FusedPWCLONet:
         # kernel here already fills the machine (the kNN CTAs take 1024 threads x 63 registers, nothing co-resides),
         # so the streams only interleave whole kernels and the geometry chain, which is the critical path, loses SMs
         # to the layers.  Off by default.
-        self.overlap = os.environ.get("PWCLO_OVERLAP", "0") == "1"
-        self._side = torch.cuda.Stream(device=dev) if self.overlap else None
+        # ... but with FEW clouds (a sharded batch of 8 pairs, one odometry pair) the FPS chain occupies 2B SMs for
+        # ~1.3 ms while everything else waits: there the second stream lets the level-l set conv / kNN run beside the
+        # level-(l+1) sampling.  PWCLO_OVERLAP = 1 / 0 forces it on / off; default: on when 2B <= OVERLAP_MAX_CLOUDS.
+        ov = os.environ.get("PWCLO_OVERLAP", "")
+        self.overlap_mode = {"1": True, "0": False}.get(ov)
+        self.overlap = False
+        self._side = torch.cuda.Stream(device=dev)
 
     # ------------------------------------------------------------------ thin launch helpers
     def _call(self, name, *args, note="", work=(0, 0)):
@@ -352,6 +362,7 @@ class FusedPWCLONet:
 
     # ------------------------------------------------------------------ the whole forward as ONE CUDA graph
     MAX_GRAPHS = 4
+    OVERLAP_MAX_CLOUDS = 48
 
     def forward_graphed(self, xyz_f1, xyz_f2):
         """forward() replayed from a CUDA graph captured once per input shape (every shape on the path is static:
@@ -360,7 +371,7 @@ class FusedPWCLONet:
         (ctypes + ~60 torch.empty) is what bounds batches of a few pairs -- the sharded batch at 8 GPUs, the odometry
         adapter at one pair.  Inputs are copied into the graph's static buffers (this replaces forward()'s torch.cat),
         outputs are cloned out of them, so results stay valid across calls like any torch result."""
-        if (not self.use_graph or self.timeline is not None or self.overlap or not xyz_f1.is_cuda
+        if (not self.use_graph or self.timeline is not None or not xyz_f1.is_cuda
                 or xyz_f1.dtype != torch.float32 or xyz_f2.dtype != torch.float32 or xyz_f1.shape != xyz_f2.shape):
             return self.forward(xyz_f1, xyz_f2)
         key = (xyz_f1.shape[0], xyz_f1.shape[2])
@@ -410,6 +421,8 @@ class FusedPWCLONet:
         """xyz_f1, xyz_f2: [B,3,N] fp32 CUDA -> (pose_params [B,4,7], embedding_mask_1 [B,64,2048] view,
         new_xyz_f1_1 [B,2048,3]).  _cat: the two frames already stacked as [2B,3,N] (forward_graphed)."""
         B = xyz_f1.shape[0] if _cat is None else _cat.shape[0] // 2
+        self.overlap = (self.overlap_mode if self.overlap_mode is not None else 2 * B <= self.OVERLAP_MAX_CLOUDS) \
+            and self.timeline is None
         self._sorted = {}          # (data_ptr, clouds, points) -> sorted kNN workspace, valid for this forward only
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)

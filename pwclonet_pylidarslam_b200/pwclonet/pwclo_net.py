@@ -183,10 +183,11 @@ class PWCLONet(nn.Module):
         # calls: train-mode BatchNorm statistics must be those of one frame's batch, as in the reference.
         Bp = xyz_f1_t.shape[0]
         geoms, cur = [], torch.cat((xyz_f1_t, xyz_f2_t), dim=0).detach()
-        tie = None          # FPS of an FPS-ordered, tie-free cloud is 0..m-1: levels 2-4 skip their rounds (same indices)
+        # (the FPS prefix shortcut -- geometry(tie_in=..., return_tie=True) -- is not used: measured, tracking ties costs more
+        # on level 1 than the skipped levels give back as soon as one cloud of the batch has a tie; see fused.py)
         for psa in (self.psa_1, self.psa_2, self.psa_3, self.psa_4):
-            *g, tie = psa.geometry(cur, tie_in=tie, return_tie=True)
-            geoms.append(tuple(g))
+            g = psa.geometry(cur)
+            geoms.append(g)
             cur = g[1]
         for psa, g in zip((self.psa_1, self.psa_2, self.psa_3, self.psa_4), geoms):
             a, b = psa(x1[-1], f1[-1], geom=tuple(t[:Bp] for t in g))
