@@ -50,7 +50,7 @@ __device__ __forceinline__ bool fps_prefix_shortcut(const int32_t* __restrict__ 
   return true;
 }
 
-template <int P, int THREADS, int MODE, bool TIE>
+template <int P, int THREADS, int MODE, bool TIE, int PICK>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origin_skip, float* __restrict__ scratch,
            int32_t* __restrict__ idx, const int32_t* __restrict__ tie_in, int32_t* __restrict__ tie_out) {
@@ -105,6 +105,70 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origin_ski
   }
   if (tid == 0) idx[0] = 0;
   __syncthreads();
+
+  if (PICK == 2 && MODE == 0) {          // double pick, see fps_slab_kernel
+    __shared__ unsigned red2_val[2][2][32], red2_key[2][2][32];
+    int sa = 0, sb = 0;
+    bool have_b = false;
+    for (int r = 1, it = 0; r < m; ++it) {
+      const float xa = sx[sa], ya = sy[sa], za = sz[sa];
+      const float xb = sx[sb], yb = sy[sb], zb = sz[sb];
+      float best = -1.0f;
+      int bj = 0;
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        float d2 = fminf(dist2_ref_fma(px[j] - xa, py[j] - ya, pz[j] - za), mind[j]);
+        if (have_b) d2 = fminf(d2, dist2_ref_fma(px[j] - xb, py[j] - yb, pz[j] - zb));
+        mind[j] = d2;
+        if (d2 > best) { best = d2; bj = j; }
+      }
+      const unsigned vb = best < 0.f ? 0u : __float_as_uint(best) + 1u;
+      const unsigned key = fps_key((unsigned)(tid + bj * THREADS), logT);
+      const unsigned wv1 = __reduce_max_sync(PWCLO_FULL_MASK, vb);
+      const unsigned wk1 = __reduce_min_sync(PWCLO_FULL_MASK, vb == wv1 ? key : 0xffffffffu);
+      const bool owner = wv1 != 0u && vb == wv1 && key == wk1;
+      float sbest = -1.0f;
+      int sj = 0;
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        const float v = (owner && j == bj) ? -2.0f : mind[j];
+        if (v > sbest) { sbest = v; sj = j; }
+      }
+      const unsigned vs = sbest < 0.f ? 0u : __float_as_uint(sbest) + 1u;
+      const unsigned skey = fps_key((unsigned)(tid + sj * THREADS), logT);
+      const unsigned wv2 = __reduce_max_sync(PWCLO_FULL_MASK, vs);
+      const unsigned wk2 = __reduce_min_sync(PWCLO_FULL_MASK, (vs == wv2 && wv2 != 0u) ? skey : 0xffffffffu);
+      const int buf = it & 1;
+      if (lane == 0) {
+        red2_val[buf][0][warp] = wv1; red2_key[buf][0][warp] = wk1;
+        red2_val[buf][1][warp] = wv2; red2_key[buf][1][warp] = wk2;
+      }
+      __syncthreads();
+      const unsigned v1 = lane < NW ? red2_val[buf][0][lane] : 0u, k1 = lane < NW ? red2_key[buf][0][lane] : 0xffffffffu;
+      const unsigned v2 = lane < NW ? red2_val[buf][1][lane] : 0u, k2 = lane < NW ? red2_key[buf][1][lane] : 0xffffffffu;
+      const unsigned bv1 = __reduce_max_sync(PWCLO_FULL_MASK, v1);
+      const unsigned bk1 = __reduce_min_sync(PWCLO_FULL_MASK, v1 == bv1 ? k1 : 0xffffffffu);
+      const bool win = bv1 != 0u && v1 == bv1 && k1 == bk1;
+      const unsigned cv2 = win ? v2 : v1, ck2 = win ? k2 : k1;
+      const unsigned bv2 = __reduce_max_sync(PWCLO_FULL_MASK, cv2);
+      const unsigned bk2 = __reduce_min_sync(PWCLO_FULL_MASK, cv2 == bv2 ? ck2 : 0xffffffffu);
+      sa = bv1 == 0u ? 0 : (int)fps_key_to_index(bk1, logT);
+      if (tid == 0) idx[r] = sa;
+      have_b = false;
+      sb = sa;
+      if (bv1 != 0u && bv2 > 1u && r + 1 < m) {
+        const int cand = (int)fps_key_to_index(bk2, logT);
+        const float d = dist2_ref_fma(sx[cand] - sx[sa], sy[cand] - sy[sa], sz[cand] - sz[sa]);
+        if (!(d < __uint_as_float(bv2 - 1u))) {
+          have_b = true;
+          sb = cand;
+          if (tid == 0) idx[r + 1] = cand;
+        }
+      }
+      r += have_b ? 2 : 1;
+    }
+    return;
+  }
 
   int old = 0;
   for (int r = 1; r < m; ++r) {
@@ -222,7 +286,13 @@ __device__ __forceinline__ void fps_bitonic_sort32(unsigned* keys, int tid) {
   }
 }
 
-template <int P, int THREADS, bool TIE>
+// PICK = 2 ("double pick", exact): a round also finds the SECOND candidate b in the reference's order.  If selecting the
+// winner a cannot lower b's running minimum (d(b, a) >= mind[b], the very comparison the next round's update would
+// make) and mind[b] > 0, then after a's update every other point still ranks behind b (minima only decrease, a itself
+// drops to 0), so b IS the next sample: both indices are written now and the next round applies both updates in one
+// pass.  The sampling is a 2047-deep dependent chain bound by the barrier + reduction latency of a round, not by the
+// distance updates.  Bit-identical output -- but measured slower on LiDAR clouds (see launch_fps_slab), so it is opt-in.
+template <int P, int THREADS, bool TIE, int PICK>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_slab_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origin_skip, int32_t* __restrict__ idx, int dbg,
                 const int32_t* __restrict__ tie_in, int32_t* __restrict__ tie_out) {
@@ -339,6 +409,108 @@ fps_slab_kernel(const float* __restrict__ xyz, int n, int m, int logT, int origi
   }
   __syncthreads();
 
+  if (PICK == 2) {
+    __shared__ unsigned red2_val[2][2][32], red2_key[2][2][32];      // [buffer][first / second of the warp][warp]
+    unsigned wv1 = 0u, wk1 = 0xffffffffu, wv2 = 0u, wk2 = 0xffffffffu;   // cached warp top-2 (value, key)
+    float wmax = 1e10f;
+    int sa = 0, sb = 0;                  // the sample(s) selected by the previous round
+    bool have_b = false;
+    const int* my_idx = sidx + warp * 32 * P + lane;
+    for (int r = 1, it = 0; r < m; ++it) {
+      const float xa = sx[sa], ya = sy[sa], za = sz[sa];
+      const float xb = sx[sb], yb = sy[sb], zb = sz[sb];
+      const float qa = axis == 0 ? xa : (axis == 1 ? ya : za);
+      const float qb = axis == 0 ? xb : (axis == 1 ? yb : zb);
+      const float dma = fmaxf(fmaxf(__fsub_rn(slab_lo, qa), __fsub_rn(qa, slab_hi)), 0.f);
+      const float dmb = fmaxf(fmaxf(__fsub_rn(slab_lo, qb), __fsub_rn(qb, slab_hi)), 0.f);
+      if (!(__fmul_rn(dma, dma) > wmax) || (have_b && !(__fmul_rn(dmb, dmb) > wmax))) {   // warp-uniform: the slab may change
+        float cv[P];
+        int cj[P];
+        if (have_b) {
+#pragma unroll
+          for (int j = 0; j < P; ++j) {
+            const float da = dist2_ref_fma(px[j] - xa, py[j] - ya, pz[j] - za);
+            const float db = dist2_ref_fma(px[j] - xb, py[j] - yb, pz[j] - zb);
+            const float d2 = fminf(fminf(da, mind[j]), db);
+            mind[j] = d2; cv[j] = d2; cj[j] = j;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < P; ++j) {
+            const float d2 = fminf(dist2_ref_fma(px[j] - xa, py[j] - ya, pz[j] - za), mind[j]);
+            mind[j] = d2; cv[j] = d2; cj[j] = j;
+          }
+        }
+#pragma unroll
+        for (int w = 1; w < P; w <<= 1) {
+#pragma unroll
+          for (int j = 0; j + w < P; j += 2 * w) {
+            const bool take = cv[j + w] > cv[j];
+            cv[j] = take ? cv[j + w] : cv[j];
+            cj[j] = take ? cj[j + w] : cj[j];
+          }
+        }
+        const float best = cv[0] > -1.0f ? cv[0] : -1.0f;
+        const int bj = cv[0] > -1.0f ? cj[0] : 0;
+        const unsigned vb = best < 0.f ? 0u : __float_as_uint(best) + 1u;
+        wv1 = __reduce_max_sync(PWCLO_FULL_MASK, vb);
+        unsigned key = 0xffffffffu;
+        if (vb == wv1) key = fps_key((unsigned)my_idx[bj * 32], logT);
+        wk1 = __reduce_min_sync(PWCLO_FULL_MASK, key);
+        wmax = wv1 == 0u ? -1.0f : __uint_as_float(wv1 - 1u);
+        // second of the warp: the owner lane of the first repeats its tournament without that point; the other lanes'
+        // candidates are their own first (masking nothing reproduces it)
+        const bool owner = wv1 != 0u && vb == wv1 && key == wk1;
+#pragma unroll
+        for (int j = 0; j < P; ++j) { cv[j] = (owner && j == bj) ? -2.0f : mind[j]; cj[j] = j; }
+#pragma unroll
+        for (int w = 1; w < P; w <<= 1) {
+#pragma unroll
+          for (int j = 0; j + w < P; j += 2 * w) {
+            const bool take = cv[j + w] > cv[j];
+            cv[j] = take ? cv[j + w] : cv[j];
+            cj[j] = take ? cj[j + w] : cj[j];
+          }
+        }
+        const float sbest = cv[0] > -1.0f ? cv[0] : -1.0f;
+        const int sj = cv[0] > -1.0f ? cj[0] : 0;
+        const unsigned vs = sbest < 0.f ? 0u : __float_as_uint(sbest) + 1u;
+        wv2 = __reduce_max_sync(PWCLO_FULL_MASK, vs);
+        unsigned key2 = 0xffffffffu;
+        if (vs == wv2 && wv2 != 0u) key2 = fps_key((unsigned)my_idx[sj * 32], logT);
+        wk2 = __reduce_min_sync(PWCLO_FULL_MASK, key2);
+      }
+      const int buf = it & 1;
+      if (lane == 0) {
+        red2_val[buf][0][warp] = wv1; red2_key[buf][0][warp] = wk1;
+        red2_val[buf][1][warp] = wv2; red2_key[buf][1][warp] = wk2;
+      }
+      __syncthreads();
+      const unsigned v1 = lane < NW ? red2_val[buf][0][lane] : 0u, k1 = lane < NW ? red2_key[buf][0][lane] : 0xffffffffu;
+      const unsigned v2 = lane < NW ? red2_val[buf][1][lane] : 0u, k2 = lane < NW ? red2_key[buf][1][lane] : 0xffffffffu;
+      const unsigned bv1 = __reduce_max_sync(PWCLO_FULL_MASK, v1);
+      const unsigned bk1 = __reduce_min_sync(PWCLO_FULL_MASK, v1 == bv1 ? k1 : 0xffffffffu);
+      const bool win = bv1 != 0u && v1 == bv1 && k1 == bk1;           // the warp that holds the first: its second competes
+      const unsigned cv2 = win ? v2 : v1, ck2 = win ? k2 : k1;
+      const unsigned bv2 = __reduce_max_sync(PWCLO_FULL_MASK, cv2);
+      const unsigned bk2 = __reduce_min_sync(PWCLO_FULL_MASK, cv2 == bv2 ? ck2 : 0xffffffffu);
+      sa = bv1 == 0u ? 0 : (int)fps_key_to_index(bk1, logT);
+      if (tid == 0) idx[r] = sa;
+      have_b = false;
+      sb = sa;
+      if (bv1 != 0u && bv2 > 1u && r + 1 < m) {            // a second candidate with a running minimum > 0
+        const int cand = (int)fps_key_to_index(bk2, logT);
+        const float d = dist2_ref_fma(sx[cand] - sx[sa], sy[cand] - sy[sa], sz[cand] - sz[sa]);   // candidate minus last
+        if (!(d < __uint_as_float(bv2 - 1u))) {            // fminf(d, mind[cand]) would leave mind[cand] unchanged
+          have_b = true;
+          sb = cand;
+          if (tid == 0) idx[r + 1] = cand;
+        }
+      }
+      r += have_b ? 2 : 1;
+    }
+    return;
+  }
   unsigned wv = 0u, wk = 0xffffffffu;   // cached warp (value, key)
   float wmax = 1e10f;                   // cached largest running minimum of the warp (-1: no valid point)
   int old = 0;
@@ -415,7 +587,13 @@ template <int P, int THREADS>
 static int launch_fps_slab(const float* xyz, int B, int n, int m, int logT, int origin_skip, int32_t* idx, FpsTie tie,
                            cudaStream_t st) {
   const size_t smem = (size_t)P * THREADS * (sizeof(unsigned) + sizeof(int)) + (size_t)3 * n * sizeof(float);
-  auto kern = tie.out ? fps_slab_kernel<P, THREADS, true> : fps_slab_kernel<P, THREADS, false>;
+  const char* pe = getenv("PWCLO_FPS_PICK");
+  // Measured on the B200 (profiles/r2f_fps_double_pick.json): the double pick is exact but SLOWER (8192 -> 2048: 1.15 ms
+  // against 0.89 ms) -- the two best candidates of a round usually sit in the same gap of the sample set, so the second
+  // one is rarely independent of the first, and the top-2 bookkeeping lengthens every round.  Opt-in: PWCLO_FPS_PICK=2.
+  const bool dual = pe && pe[0] == '2';
+  auto kern = tie.out ? fps_slab_kernel<P, THREADS, true, 1>
+                      : (dual ? fps_slab_kernel<P, THREADS, false, 2> : fps_slab_kernel<P, THREADS, false, 1>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<B, THREADS, smem, st>>>(xyz, n, m, logT, origin_skip, idx, getenv("PWCLO_FPS_DBG_SKIPALL") ? 1 : 0, tie.in, tie.out);
@@ -580,7 +758,10 @@ template <int P, int THREADS, int MODE>
 static int launch_fps(const float* xyz, int B, int n, int m, int logT, int origin_skip, float* scratch, int32_t* idx,
                       FpsTie tie, cudaStream_t st) {
   size_t smem = MODE == 2 ? 0 : (size_t)3 * n * sizeof(float);
-  auto kern = tie.out ? fps_kernel<P, THREADS, MODE, true> : fps_kernel<P, THREADS, MODE, false>;
+  const char* pe = getenv("PWCLO_FPS_PICK");
+  const bool dual = MODE == 0 && pe && pe[0] == '2';
+  auto kern = tie.out ? fps_kernel<P, THREADS, MODE, true, 1>
+                      : (dual ? fps_kernel<P, THREADS, MODE, false, 2> : fps_kernel<P, THREADS, MODE, false, 1>);
   if (smem > 32 * 1024) {  // static smem (reduction slots) counts against the 48 KB default limit
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

@@ -57,6 +57,22 @@ def test_fps_bit_exact(cuda, ref_ext, B, N, m, kind):
         np.testing.assert_array_equal(got, ref)
 
 
+@pytest.mark.parametrize("B,N,m,kind", [(3, 8192, 2048, "lidar"), (2, 8192, 2048, "dups"), (1, 4096, 1024, "grid"), (2, 2048, 1024, "origin"),
+                                        (2, 2048, 1024, "rand"), (3, 1024, 256, "dups"), (4, 256, 64, "rand"), (2, 300, 299, "dups"),
+                                        (1, 5000, 4999, "rand"), (2, 64, 64, "rand")])
+def test_fps_double_pick_equals_single_pick(cuda, monkeypatch, B, N, m, kind):
+    """PWCLO_FPS_PICK=2 selects up to two samples per round (exact: the second candidate is taken only when the first
+    cannot lower its running minimum; opt-in, measured slower).  Same indices as the default one-sample rounds, and both
+    equal the C restatement of the reference kernel -- duplicates, lattice ties, origin-ball points, m == N included."""
+    x = _fps_input(kind, B, N, seed=11 * N + m)
+    d = _dev(x, cuda)
+    one = _ext.furthest_point_sampling(d, m).cpu().numpy()
+    monkeypatch.setenv("PWCLO_FPS_PICK", "2")
+    two = _ext.furthest_point_sampling(d, m).cpu().numpy()
+    np.testing.assert_array_equal(two, one)
+    np.testing.assert_array_equal(two, cpu_ops.fps(x, m, origin_skip=True, thread_cap=512))
+
+
 PREFIX_CASES = [
     # (B, N, kind, cluster): the pyramid chain N -> 2048|N/4 -> /2 -> /4 -> /4 of PW/pwclo_net.py:66-69 on every input kind
     (3, 8192, "lidar", "0"), (2, 8192, "rand", "0"), (2, 8192, "dups", "0"), (2, 8192, "origin", "0"), (1, 4096, "grid", "0"),

@@ -24,7 +24,9 @@ x1, x2, gt = syn.make_batch(900 + 10 * local, 2, 4096)
 batch = [torch.from_numpy(np.ascontiguousarray(x1.transpose(0, 2, 1))).to(dev), torch.from_numpy(np.ascontiguousarray(x2.transpose(0, 2, 1))).to(dev),
          torch.from_numpy(gt[:, 3:]).to(dev), torch.from_numpy(gt[:, :3]).to(dev)]
 batch2 = [b.flip(0).contiguous() for b in batch]
-cfg = T.PWCLONetTrainerConfig(num_points=4096, device=str(dev))
+# a small learning rate keeps the comparison about the step, not about how fast two trajectories diverge under the
+# run-to-run noise of the scatter-add atomics
+cfg = T.PWCLONetTrainerConfig(num_points=4096, device=str(dev), optimizer_learning_rate=1e-5)
 torch.manual_seed(0)
 a = T.PWCLONetTrainer(cfg)
 b = T.PWCLONetTrainer(cfg)
@@ -40,7 +42,7 @@ for i in range(4):
     eager.append(float(a.train_step(bt)[0]))
     graphed.append(float(b.train_step_graphed(bt)[0]))
 print(f"rank {local}: eager {eager[2:]} graphed {graphed}", flush=True)
-np.testing.assert_allclose(graphed, eager[2:], rtol=1e-3)
+np.testing.assert_allclose(graphed, eager[2:], rtol=2e-4)
 # both ranks hold the same parameters after data-parallel steps
 p = b.arena.param.clone()
 dist.all_reduce(p, op=dist.ReduceOp.MAX)
