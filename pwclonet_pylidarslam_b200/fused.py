@@ -211,6 +211,7 @@ class FusedPWCLONet:
         self.overlap_mode = {"1": True, "0": False}.get(ov)
         self.overlap = False
         self._side = torch.cuda.Stream(device=dev)
+        self._branch = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))   # the two set-upconvs of a level
 
     # ------------------------------------------------------------------ thin launch helpers
     def _call(self, name, *args, note="", work=(0, 0)):
@@ -487,19 +488,45 @@ class FusedPWCLONet:
                     trace[f"psa{l}.fps_idx"], trace[f"psa{l}.knn_idx"] = lvl_idx[l - 1]
 
             emb_prev, mask_prev = emb4, mask4
+            keep = []      # few-cloud mode: nothing allocated on a branch stream is recycled before the forward ends
             for l in (3, 2, 1):
                 p = f"pose_warp_refinement_{l}"
                 need(up_ev[l])
-                m_f = self.set_conv(f"{p}.setupconv_features.mlp", X1[l + 1], emb_prev, X1[l], up_idx[l])
-                cf = self.pointwise(f"{p}.setupconv_features.post_mlp", [m_f, F1[l]])
-                m_m = self.set_conv(f"{p}.setupconv_mask.mlp", X1[l + 1], mask_prev, X1[l], up_idx[l])
-                cm = self.pointwise(f"{p}.setupconv_mask.post_mlp", [m_m, F1[l]])
+
+                def upconv(which, prev):
+                    m = self.set_conv(f"{p}.setupconv_{which}.mlp", X1[l + 1], prev, X1[l], up_idx[l])
+                    return m, self.pointwise(f"{p}.setupconv_{which}.post_mlp", [m, F1[l]])
+
+                if side is None:
+                    m_f, cf = upconv("features", emb_prev)
+                    m_m, cm = upconv("mask", mask_prev)
+                    joins = ()
+                else:
+                    # the two set-upconvs depend on the previous level's outputs only, the searches and the cost volume on
+                    # its pose only: three branches of the captured graph instead of an 11-kernel chain
+                    ev0 = torch.cuda.Event()
+                    ev0.record(main)
+                    joins = []
+                    outs = []
+                    for st, which, prev in ((self._branch[0], "features", emb_prev), (self._branch[1], "mask", mask_prev)):
+                        st.wait_event(ev0)
+                        with torch.cuda.stream(st):
+                            outs.append(upconv(which, prev))
+                            ev = torch.cuda.Event()
+                            ev.record(st)
+                            joins.append(ev)
+                    (m_f, cf), (m_m, cm) = outs
                 idx_q, warped = self.knn(X2[l], X1[l], 6, warp_qt=qt)           # pose warp fused into the search
                 idx_s = self.knn(warped, warped, 4)
-                res, _ = self.cost_volume(f"{p}.cost_volume", warped, F1[l], X2[l], F2[l], idx_q, idx_s)
+                res, e1 = self.cost_volume(f"{p}.cost_volume", warped, F1[l], X2[l], F2[l], idx_q, idx_s)
+                if joins:
+                    main.wait_event(joins[0])
                 ef = self.pointwise(f"{p}.flow_predictor_features.mlp_convs", [F1[l], res, cf])
+                if joins:
+                    main.wait_event(joins[1])
                 em = cm if l == 1 else self.pointwise(f"{p}.flow_predictor_mask.mlp_convs", [cm, ef, F1[l]])
                 qt = self.pose_head(f"{p}.pose_calculator", ef, em, qt, pose, l - 1)
+                keep += [m_f, cf, m_m, cm, idx_q, warped, idx_s, res, e1, ef, em, qt]
                 if trace is not None:
                     trace.update({f"pwr{l}.up_f": cf, f"pwr{l}.up_m": cm, f"pwr{l}.warped": warped, f"pwr{l}.cv": res,
                                   f"pwr{l}.emb": ef, f"pwr{l}.mask": em, f"pwr{l}.qt": qt, f"pwr{l}.idx_q": idx_q,
