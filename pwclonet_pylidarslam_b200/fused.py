@@ -281,6 +281,24 @@ class FusedPWCLONet:
                        None, note=note, work=work)
         return (idx, warped) if warp_qt is not None else idx
 
+    def presort(self, xyz, k):
+        """sort the clouds `xyz` [B,N,3] for later searches of this forward (pwclo_knn_presort) and remember the workspace
+        for the whole batch and for its two halves (frame 1 / frame 2)"""
+        B, N, _ = xyz.shape
+        if not (_ext.KNN_SORTED and N >= _ext.KNN_SORTED_MIN_N) or B % 2 or os.environ.get("PWCLO_KNN_QORDER"):
+            return
+        ws_bytes = self.lib.pwclo_knn_workspace_bytes(B, N, 0)
+        if not ws_bytes or (xyz.data_ptr(), B, N) in self._sorted:
+            return
+        ws = self._new(ws_bytes, dtype=torch.uint8)
+        self._call("pwclo_knn_presort", _p(xyz), B, N, k, _p(ws), ws_bytes,
+                   note=f"[B{B} N{N}]" if self.verbose_timeline else "", work=(4 * B * 3 * N, 0))
+        rec = self.lib.pwclo_knn_workspace_bytes(1, N, 0)
+        h = B // 2
+        self._sorted[(xyz.data_ptr(), B, N)] = ws
+        self._sorted[(xyz[:h].data_ptr(), h, N)] = ws[:h * rec]
+        self._sorted[(xyz[h:].data_ptr(), h, N)] = ws[h * rec:B * rec]
+
     def set_conv(self, key, xyz, feats, new_xyz, idx):
         B, N, _ = xyz.shape
         S, K = idx.shape[1], idx.shape[2]
@@ -446,36 +464,39 @@ class FusedPWCLONet:
             xyz = self.to_point_major(torch.cat((xyz_f1, xyz_f2), dim=0).float() if _cat is None else _cat)
             if side is not None:
                 side.wait_stream(main)      # inputs are ready; also orders this forward's geometry after the previous forward
-            xs, lvl_idx, lvl_ev = [xyz], [], []
+            # Few-cloud mode: the side stream carries ONLY the dependent sampling chain (FPS -> gather per level, ~1.3 ms
+            # on 2B SMs); the neighbour searches and set convs of level l run on the main stream as soon as level l's
+            # centres exist, i.e. beside the sampling of levels l+1...  With many clouds everything is one stream.
+            xs, fidxs, lvl_ev = [xyz], [], []
             with geo:
                 tie = None
                 for l, (npoint, k) in enumerate(self.LEVELS):
                     fidx, tie = self.fps(xs[-1], npoint, tie)
-                    new_xyz = self.gather3(xs[-1], fidx)
-                    idx = self.knn(xs[-1], new_xyz, k, keep_sorted=l >= 1)      # levels 1-3 are searched again below
-                    lvl_idx.append((fidx, idx))
+                    xs.append(self.gather3(xs[-1], fidx))
+                    fidxs.append(fidx)
                     lvl_ev.append(mark())
-                    xs.append(new_xyz)
-                X1 = [None] + [x[:B] for x in xs[1:]]
-                X2 = [None] + [x[B:] for x in xs[1:]]
-                # the remaining coordinate-only searches: coarse cost volume (level 3) and the three set-upconvs
-                idx_q3 = self.knn(X2[3], X1[3], 32)
-                idx_s3 = self.knn(X1[3], X1[3], 4)
-                ev_cv3 = mark()
-                up_idx, up_ev = {}, {}
-                for l in (3, 2, 1):
-                    up_idx[l] = self.knn(X1[l + 1], X1[l], 8)
-                    up_ev[l] = mark()
-            fs = [None]
-            for l in range(len(self.LEVELS)):
+            X1 = [None] + [x[:B] for x in xs[1:]]
+            X2 = [None] + [x[B:] for x in xs[1:]]
+            fs, lvl_idx, up_idx = [None], [], {}
+            for l, (npoint, k) in enumerate(self.LEVELS):
                 need(lvl_ev[l])
-                fs.append(self.set_conv(f"psa_{l + 1}.mlp_module", xs[l], fs[-1], xs[l + 1], lvl_idx[l][1]))
+                idx = self.knn(xs[l], xs[l + 1], k, keep_sorted=l >= 1)          # levels 1-3 are searched again below
+                lvl_idx.append((fidxs[l], idx))
+                fs.append(self.set_conv(f"psa_{l + 1}.mlp_module", xs[l], fs[-1], xs[l + 1], idx))
+                if l < 3:       # the centres of this level are the reference cloud of several later searches: sort them once, now
+                    self.presort(xs[l + 1], self.LEVELS[l + 1][1])
+                if l == 2:      # coordinate-only searches whose inputs exist now: coarse cost volume (level 3), upconvs 2 and 1
+                    idx_q3 = self.knn(X2[3], X1[3], 32)
+                    idx_s3 = self.knn(X1[3], X1[3], 4)
+                    up_idx[2] = self.knn(X1[3], X1[2], 8)
+                    up_idx[1] = self.knn(X1[2], X1[1], 8)
+            up_idx[3] = self.knn(X1[4], X1[3], 8)
+            up_ev = {3: None, 2: None, 1: None}
             F1 = [None] + [f[:B] for f in fs[1:]]
             F2 = [None] + [f[B:] for f in fs[1:]]
             pose = self._new(B, 4, 7)
 
             # coarse cost volume at level 3 + flow feature encoding (PW/pwclo_net.py:162-167)
-            need(ev_cv3)
             emb, _ = self.cost_volume("cost_volume", X1[3], F1[3], X2[3], F2[3], idx_q3, idx_s3)
             # flow_feature_encoding re-runs FPS + kNN on xyz1 of level 3: identical to psa_4's (frame 1)
             emb4 = self.set_conv("flow_feature_encoding.mlp_module", X1[3], emb, X1[4], lvl_idx[3][1][:B])
