@@ -274,7 +274,7 @@ def build_net(dev, weights):
 def measure_forward(ctx, net, h1, h2, steps, warmup, pairs_total):
     """resident-input throughput + streaming e2e for this rank's shard (h1, h2 host arrays [p,3,N]); every rank calls it.
     Returns dict(ms_total, ms_e2e, ms_e2e_serial, launches, pose, pin bytes) with times already max-reduced."""
-    from pwclonet_pylidarslam_b200.sharding import PosePipeline
+    from pwclonet_pylidarslam_b200.sharding import ForwardStreams, PosePipeline, auto_compute_streams
     dev = ctx.dev
     pin1, pin2 = torch.from_numpy(h1).pin_memory(), torch.from_numpy(h2).pin_memory()
     d1, d2 = pin1.to(dev), pin2.to(dev)
@@ -296,9 +296,37 @@ def measure_forward(ctx, net, h1, h2, steps, warmup, pairs_total):
     ctx.barrier()
     sampler.start()
     launches0 = eng.launches
-    ms_total, pose = ctx.timed(step_resident, steps)
+    ms_serial, pose = ctx.timed(step_resident, steps)      # one forward at a time, L2 flush outside the events
     launches = eng.launches - launches0
     ctx.barrier()
+    in_flight = auto_compute_streams(h1.shape[0])
+    if in_flight > 1:
+        # few pairs per GPU: the public streaming path keeps two forwards in flight (sharding.ForwardStreams), so the
+        # sampling chain of step i+1 (one SM per cloud) runs beside the layers of step i.  K steps are timed as ONE
+        # bracket; the L2 flush of every step is enqueued on its own stream (there is no "between" two overlapped steps).
+        fwd = ForwardStreams(net, in_flight)
+        flush_stream = torch.cuda.Stream(device=dev)
+
+        def streamed(k):
+            for _ in range(k):
+                with torch.cuda.stream(flush_stream):
+                    ctx.flush.zero_()
+                fwd.submit(d1, d2)
+            fwd.join()
+
+        streamed(max(3, warmup))
+        ctx.barrier()
+        launches0 = eng.launches
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
+        streamed(steps)
+        e_ev.record()
+        torch.cuda.synchronize()
+        ms_total = s_ev.elapsed_time(e_ev)
+        launches = eng.launches - launches0
+        ctx.barrier()
+    else:
+        ms_total = ms_serial
     sampler.stop_flag = True
     # e2e: the streaming public API (sharding.PosePipeline): every step's two clouds are copied from pinned host
     # memory and its pose is read back to the host inside the timed region; the copy of step i+1 overlaps the
@@ -325,8 +353,9 @@ def measure_forward(ctx, net, h1, h2, steps, warmup, pairs_total):
     step_e2e()
     ms_e2e_serial, _ = ctx.timed(step_e2e, steps)      # copy -> forward -> read back, nothing overlapped
     ctx.barrier()
-    ms_total_max, ms_e2e_max, ms_serial_max = ctx.max_over_ranks([ms_total, ms_e2e, ms_e2e_serial])
+    ms_total_max, ms_e2e_max, ms_serial_max, ms_fwd_serial = ctx.max_over_ranks([ms_total, ms_e2e, ms_e2e_serial, ms_serial])
     return {"ms_total": ms_total_max, "ms_e2e": ms_e2e_max, "ms_e2e_serial": ms_serial_max, "ms_total_rank": ms_total,
+            "in_flight": in_flight, "ms_forward_serial": ms_fwd_serial / steps,
             "launches": int(launches), "pose": pose, "h2d": int(pin1.numel() * 4 * 2), "d2h": int(pose.numel() * 4),
             "clocks": sampler.summary(), "step_resident": step_resident,
             "value": pairs_total * steps / (ms_total_max * 1e-3), "e2e": pairs_total * steps / (ms_e2e_max * 1e-3),
@@ -704,8 +733,12 @@ def main():
                                           else f"({T} pairs on every one of {world} GPUs)")
                                        + ", synthetic KITTI-64-beam clouds, random-init weights with non-trivial BN statistics",
                            "total_pairs": pairs_total, "pairs_per_gpu": per_gpu, "points": N_POINTS,
-                           "l2": "flushed between timed steps (256 MB write)",
-                           "execution": "whole forward replayed as one CUDA graph per step",
+                           "l2": ("flushed between timed steps (256 MB write)" if m["in_flight"] == 1 else
+                                  "256 MB flush write enqueued once per step on its own stream (steps overlap: no 'between')"),
+                           "execution": ("whole forward replayed as one CUDA graph per step" if m["in_flight"] == 1 else
+                                         f"whole forward = one CUDA graph; {m['in_flight']} steps in flight on {m['in_flight']} streams "
+                                         "(sharding.ForwardStreams): K steps timed as one bracket, value = throughput"),
+                           "steps_in_flight": m["in_flight"], "forward_latency_ms": m["ms_forward_serial"],
                            "parallelism": f"frame-pair sharding x{world}, no data-path collective"},
                 "e2e": {"value": m["e2e"], "unit": UNIT, "h2d_bytes_per_step": m["h2d"] * (world if strong else world),
                         "d2h_bytes_per_step": m["d2h"] * world, "ms_per_step": m["ms_e2e"] / args.steps,

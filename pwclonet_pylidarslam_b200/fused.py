@@ -380,20 +380,22 @@ class FusedPWCLONet:
     LEVELS = ((2048, 32), (1024, 32), (256, 16), (64, 16))
 
     # ------------------------------------------------------------------ the whole forward as ONE CUDA graph
-    MAX_GRAPHS = 4
+    MAX_GRAPHS = 8
     OVERLAP_MAX_CLOUDS = 48
 
-    def forward_graphed(self, xyz_f1, xyz_f2):
+    def forward_graphed(self, xyz_f1, xyz_f2, slot=0):
         """forward() replayed from a CUDA graph captured once per input shape (every shape on the path is static:
         the launch list of a forward depends on (B, N) only).  The reference pays ~550 launches and a forced
         device->host sync per forward (PW/pwclo_net.py:186-193); the fused forward is ~55 launches whose host cost
         (ctypes + ~60 torch.empty) is what bounds batches of a few pairs -- the sharded batch at 8 GPUs, the odometry
         adapter at one pair.  Inputs are copied into the graph's static buffers (this replaces forward()'s torch.cat),
-        outputs are cloned out of them, so results stay valid across calls like any torch result."""
+        outputs are cloned out of them, so results stay valid across calls like any torch result.
+        `slot`: forwards that are in flight at the same time on different streams (sharding.ForwardStreams) need their
+        own static buffers: one captured graph per (shape, slot)."""
         if (not self.use_graph or self.timeline is not None or not xyz_f1.is_cuda
                 or xyz_f1.dtype != torch.float32 or xyz_f2.dtype != torch.float32 or xyz_f1.shape != xyz_f2.shape):
             return self.forward(xyz_f1, xyz_f2)
-        key = (xyz_f1.shape[0], xyz_f1.shape[2])
+        key = (xyz_f1.shape[0], xyz_f1.shape[2]) if slot == 0 else (xyz_f1.shape[0], xyz_f1.shape[2], slot)
         rec = self._graphs.get(key)
         if rec is None:
             rec = self._capture(xyz_f1, xyz_f2)

@@ -159,8 +159,10 @@ class PWCLONet(nn.Module):
         if fused_ok:
             with torch.no_grad():
                 eng = self.fused_engine()
-                run = eng.forward_graphed if self.graph_forward else eng.forward
-                pose, mask1, xyz1_l1 = run(xyz_f1, xyz_f2)
+                if self.graph_forward:
+                    pose, mask1, xyz1_l1 = eng.forward_graphed(xyz_f1, xyz_f2, slot=self.__dict__.get("fused_slot", 0))
+                else:
+                    pose, mask1, xyz1_l1 = eng.forward(xyz_f1, xyz_f2)
         else:
             pose, mask1, xyz1_l1 = self._forward_composed(xyz_f1, points_f1, xyz_f2, points_f2)
         thunks = {

@@ -46,15 +46,68 @@ def forward_sharded(net, xyz_f1, xyz_f2):
     return gather_poses(pose, total)
 
 
+class ForwardStreams:
+    """Several inference forwards in flight: forward i runs on compute stream i % n with its own captured graph and
+    static buffers (FusedPWCLONet.forward_graphed(slot=...)).  The sampling chain of a forward is ~1.3 ms of
+    latency-bound work on one SM per cloud; with few clouds per GPU (a sharded batch) it leaves most of the machine idle,
+    and the layer kernels of the previous batch fill it.  Frame pairs stay independent; results are identical."""
+
+    def __init__(self, net, n=2):
+        dev = next(net.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("ForwardStreams needs the network on a CUDA device (there is no CPU path)")
+        self.net, self.device, self.n, self.count = net, dev, max(1, int(n)), 0
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(self.n)]
+
+    def submit(self, xyz_f1, xyz_f2, after=None, then=None):
+        """enqueue one forward on the next stream (ordered after the caller's current stream and after event `after`);
+        `then(pose)` runs under that stream right behind it (e.g. the copy of the result to the host).
+        Returns (pose, event recorded on the stream once the forward and `then` are complete)."""
+        s = self.count % self.n
+        self.count += 1
+        st = self.streams[s]
+        st.wait_stream(torch.cuda.current_stream(self.device))
+        if after is not None:
+            st.wait_event(after)
+        with torch.cuda.stream(st), torch.no_grad():
+            self.net.fused_slot = s
+            try:
+                pose, _ = self.net(xyz_f1, None, xyz_f2, None)
+            finally:
+                self.net.fused_slot = 0
+            if then is not None:
+                then(pose)
+            done = torch.cuda.Event()
+            done.record(st)
+        return pose, done
+
+    def join(self):
+        """make the caller's current stream wait for everything submitted so far"""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            cur.wait_stream(st)
+
+
+def auto_compute_streams(pairs):
+    """two forwards in flight when a batch leaves most SMs idle during its sampling chain (2 clouds per pair, one SM each)"""
+    return 2 if 2 * pairs <= 64 else 1
+
+
 class PosePipeline:
     """Streaming inference for host-resident batches: the host->device copy of batch i+1 (pinned memory, own copy
     stream, second set of device buffers) overlaps the forward of batch i; the [b,4,7] result returns through a
     pinned buffer.  `run(batches)` yields one host pose tensor per batch, in order; a yielded tensor is valid until
-    `depth` further batches have been submitted.  Frame pairs stay independent: this is per-rank plumbing, the
-    sharding across GPUs is unchanged."""
+    `depth` further batches have been submitted.  With few pairs per batch two forwards are in flight on two compute
+    streams (ForwardStreams).  Frame pairs stay independent: this is per-rank plumbing, the sharding across GPUs is
+    unchanged."""
 
-    def __init__(self, net, pairs, n_points, depth=2):
+    def __init__(self, net, pairs, n_points, depth=None, compute_streams=None):
+        """compute_streams: forwards in flight (default: 2 for batches of few pairs, else 1); depth: host / device buffer
+        sets (default: compute_streams + 1)"""
+        compute_streams = auto_compute_streams(pairs) if compute_streams is None else int(compute_streams)
+        depth = compute_streams + 1 if depth is None else max(int(depth), compute_streams + 1)
         self.net, self.depth = net, depth
+        self.fwd = ForwardStreams(net, compute_streams)
         dev = next(net.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("PosePipeline needs the network on a CUDA device (there is no CPU path)")
@@ -79,12 +132,11 @@ class PosePipeline:
                 self.buf[s][0].copy_(h1, non_blocking=True)
                 self.buf[s][1].copy_(h2, non_blocking=True)
                 self.copied[s].record(self.copy_stream)
-            main.wait_event(self.copied[s])
-            with torch.no_grad():
-                pose, _ = self.net(self.buf[s][0], None, self.buf[s][1], None)
-            self.freed[s].record(main)
-            self.pose_host[s].copy_(pose, non_blocking=True)
-            self.done[s].record(main)
+            def finish(pose, s=s):       # under the forward's compute stream: inputs consumed, result to the host
+                self.freed[s].record(torch.cuda.current_stream(self.device))
+                self.pose_host[s].copy_(pose, non_blocking=True)
+
+            _, self.done[s] = self.fwd.submit(self.buf[s][0], self.buf[s][1], after=self.copied[s], then=finish)
             pending.append(s)
             if len(pending) == self.depth:          # keep depth-1 batches queued behind the one we wait for
                 s0 = pending.pop(0)

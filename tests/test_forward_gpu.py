@@ -154,3 +154,24 @@ def test_fused_cache_follows_the_weights(cuda):
         assert torch.equal(net(a, None, b, None)[0], fresh["w1"])
         parent.float().to(cuda)                                                                  # _apply
         assert net._fused is None
+
+
+def test_forward_streams_two_in_flight_equal_direct(cuda):
+    """sharding.ForwardStreams: forwards submitted back to back on two compute streams (own graph + static buffers per
+    stream) return exactly what one-at-a-time calls return, for inputs that change on every submission"""
+    from pwclonet_pylidarslam_b200 import synthetic as syn
+    from pwclonet_pylidarslam_b200.sharding import ForwardStreams
+    net, _ = _rand_net(cuda, 8)
+    ins = []
+    for i in range(6):
+        x1, x2, _ = syn.make_batch(600 + 3 * i, 3, 8192)
+        ins.append((torch.from_numpy(x1).to(cuda), torch.from_numpy(x2).to(cuda)))
+    with torch.no_grad():
+        direct = [net(a, None, b, None)[0].clone() for a, b in ins]
+    fwd = ForwardStreams(net, 2)
+    got = [fwd.submit(a, b) for a, b in ins]
+    fwd.join()
+    torch.cuda.synchronize()
+    assert len({id(s) for s in fwd.streams}) == 2 and fwd.count == 6
+    for (pose, _ev), want in zip(got, direct):
+        assert torch.equal(pose, want)
