@@ -588,7 +588,7 @@ static int launch_fps_slab(const float* xyz, int B, int n, int m, int logT, int 
                            cudaStream_t st) {
   const size_t smem = (size_t)P * THREADS * (sizeof(unsigned) + sizeof(int)) + (size_t)3 * n * sizeof(float);
   const char* pe = getenv("PWCLO_FPS_PICK");
-  // Measured on the B200 (profiles/r2f_fps_double_pick.json): the double pick is exact but SLOWER (8192 -> 2048: 1.15 ms
+  // Measured on the B200 (profiles/round2_fps_double_pick.json): the double pick is exact but SLOWER (8192 -> 2048: 1.15 ms
   // against 0.89 ms) -- the two best candidates of a round usually sit in the same gap of the sample set, so the second
   // one is rarely independent of the first, and the top-2 bookkeeping lengthens every round.  Opt-in: PWCLO_FPS_PICK=2.
   const bool dual = pe && pe[0] == '2';

@@ -186,7 +186,7 @@ class FusedPWCLONet:
         self.LT = {k: A.layers(v) for k, v in self.tc_recs.items()}
         self.use_tc = os.environ.get("PWCLO_TC", "1") != "0"
         # FPS prefix shortcut (pwclo_furthest_point_sampling_prefix): OFF by default.  Measured on the B200
-        # (tools/bench_fps_prefix.py, profiles/r2b_fps_prefix.json): tracking arg-max ties costs +40 % on the level-1
+        # (tools/bench_fps_prefix.py, profiles/round2_fps_prefix.json): tracking arg-max ties costs +40 % on the level-1
         # sampling (0.89 -> 1.26 ms: the check sits on the serial round chain), ~6 % of the synthetic LiDAR clouds do see an
         # exact fp32 tie of two running minima in 2047 rounds, and a launch lasts as long as its slowest cloud -- so with
         # 128 clouds per launch levels 2-4 (0.39 ms) are never skipped.  It pays only for single tie-free clouds.

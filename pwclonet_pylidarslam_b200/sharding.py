@@ -89,8 +89,13 @@ class ForwardStreams:
 
 
 def auto_compute_streams(pairs):
-    """two forwards in flight when a batch leaves most SMs idle during its sampling chain (2 clouds per pair, one SM each)"""
-    return 2 if 2 * pairs <= 64 else 1
+    """forwards in flight: the sampling chain of a forward (one SM per cloud, ~1.3 ms whatever the batch) overlaps the layer
+    kernels of its neighbours.  Measured on one B200 (profiles/round2_streams_sweep.txt), pairs/s with 1 / 2 / 3 in flight:
+    64 pairs 8 879 / 9 736 / 9 866; 8 pairs 3 333 / 5 198 / 6 044; 1 pair 529 / 1 044 / -.  PWCLO_STREAMS overrides."""
+    import os
+    if os.environ.get("PWCLO_STREAMS"):
+        return max(1, int(os.environ["PWCLO_STREAMS"]))
+    return 3 if pairs <= 16 else 2
 
 
 class PosePipeline:
