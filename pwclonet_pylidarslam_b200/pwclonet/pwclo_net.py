@@ -164,7 +164,9 @@ class PWCLONet(nn.Module):
                 else:
                     pose, mask1, xyz1_l1 = eng.forward(xyz_f1, xyz_f2)
         else:
-            pose, mask1, xyz1_l1 = self._forward_composed(xyz_f1, points_f1, xyz_f2, points_f2)
+            from ..pytorch_utils import deferred_bn_counters
+            with deferred_bn_counters():
+                pose, mask1, xyz1_l1 = self._forward_composed(xyz_f1, points_f1, xyz_f2, points_f2)
         thunks = {
             "embedding_mask": lambda: torch.linalg.norm(
                 F.softmax(mask1.detach().cpu(), dim=2).permute(0, 2, 1), dim=-1, ord=2),

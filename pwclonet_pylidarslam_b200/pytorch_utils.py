@@ -124,6 +124,37 @@ class SkinnyConv1x1(torch.autograd.Function):
         return dx, dw
 
 
+class deferred_bn_counters:
+    """Context: the `num_batches_tracked += 1` of every train-mode BatchNorm executed inside it (93 one-element launches
+    per training step of PWCLO-Net) is applied on exit with one multi-tensor add per distinct increment.  Same values as
+    nn.BatchNorm's own bookkeeping (a layer that ran twice -- the two frames of a pair -- counts twice)."""
+    pending = None
+
+    def __enter__(self):
+        self.outer = deferred_bn_counters.pending
+        deferred_bn_counters.pending = {} if self.outer is None else self.outer
+        return self
+
+    def __exit__(self, *exc):
+        if self.outer is None:
+            todo, deferred_bn_counters.pending = deferred_bn_counters.pending, None
+            by_count = {}
+            for t, c in todo.values():
+                by_count.setdefault(c, []).append(t)
+            for c, ts in by_count.items():
+                torch._foreach_add_(ts, c)
+        return False
+
+    @staticmethod
+    def bump(counter):
+        pend = deferred_bn_counters.pending
+        if pend is None:
+            counter.add_(1)
+        else:
+            rec = pend.setdefault(id(counter), [counter, 0])
+            rec[1] += 1
+
+
 SKINNY_CONV = os.environ.get("PWCLO_SKINNY_CONV", "1") != "0"
 FUSED_BN_RELU = os.environ.get("PWCLO_FUSED_BN", "1") != "0"
 
@@ -165,7 +196,7 @@ class _Conv(nn.Sequential):
             if norm.track_running_stats and norm.momentum is not None and norm.affine:
                 y = (SkinnyConv1x1.apply(x, self.conv.weight) if SKINNY_CONV and SkinnyConv1x1.usable(x, self.conv)
                      else self.conv(x))
-                norm.num_batches_tracked.add_(1)
+                deferred_bn_counters.bump(norm.num_batches_tracked)
                 return FusedBNReLUTrain.apply(y, norm.weight, norm.bias, norm.running_mean, norm.running_var, norm.momentum,
                                               norm.eps)
         return super().forward(x)

@@ -224,6 +224,25 @@ class FlatArena:
             p.data = self.param[o:o + n].view(p.shape)
             p.grad = self.grad[o:o + n].view(p.shape)
 
+    # -- one step without per-parameter accumulation kernels ---------------------------------------------------------
+    # With `.grad` pre-set, autograd's AccumulateGrad adds into it: one small add kernel per parameter tensor (318 per
+    # step, 6 % of the launches of a training step, profiles/round2_train_launches_summary.txt).  detach_grads() before
+    # the backward lets autograd hand over its own buffers instead; collect_grads() then gathers them into the flat
+    # arena with a handful of multi-tensor copies and restores the invariant "p.grad is a view into arena.grad".
+    def detach_grads(self):
+        for p in self.params:
+            p.grad = None
+
+    def collect_grads(self):
+        views = self.views(self.grad)
+        have = [(v, p.grad) for p, v in zip(self.params, views) if p.grad is not None]
+        if len(have) != len(views):
+            self.grad.zero_()                      # parameters the loss did not reach keep a zero gradient
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        for p, v in zip(self.params, views):
+            p.grad = v
+
     def zero_grad(self):
         self.grad.zero_()
         for p, o in zip(self.params, self.offsets):   # re-attach if something replaced a .grad
@@ -419,9 +438,15 @@ class PWCLONetTrainer:
         return loss, log, pred
 
     def _step_body(self, batch):
-        self._optimizer.zero_grad()
+        collect = os.environ.get("PWCLO_GRAD_COLLECT", "1") != "0"
+        if collect:
+            self.arena.detach_grads()
+        else:
+            self._optimizer.zero_grad()
         loss, log, pred = self.pred_loss_forward_pass(batch)
         loss.backward()
+        if collect:
+            self.arena.collect_grads()
         scale = all_reduce_gradients(self.arena)
         self._optimizer.step(grad_scale=scale)
         return loss.detach(), log, pred.detach()

@@ -97,7 +97,13 @@ def test_training_step_matches_unmodified_reference_golden(cuda, ref_ext, monkey
     net = net.to(cuda).train()
     loss_mod = T._PWCLONetLossModule(T.PWCLONetLossConfig()).to(cuda)
     monkeypatch.setattr(_ext, "KNN_SUM_ORDER", 0)       # the golden ran torch's CPU reduction order
+    nbt = {k: int(v) for k, v in net.state_dict().items() if k.endswith("num_batches_tracked")}
     pose, _ = net(torch.from_numpy(x1).to(cuda), None, torch.from_numpy(x2).to(cuda), None)
+    # nn.BatchNorm bookkeeping (applied in one multi-tensor add at the end of the forward): the siamese pyramid layers ran
+    # once per frame, everything else once
+    after = {k: int(v) for k, v in net.state_dict().items() if k.endswith("num_batches_tracked")}
+    assert all(after[k] - nbt[k] == (2 if k.startswith("psa_") else 1) for k in nbt), \
+        {k: after[k] - nbt[k] for k in nbt if after[k] - nbt[k] != (2 if k.startswith("psa_") else 1)}
     loss, _ = loss_mod(pose, torch.from_numpy(gt).to(cuda))
     loss.backward()
     te, re_ = C.pose_errors(pose.detach().cpu().numpy(), g["pose"])
