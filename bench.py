@@ -453,11 +453,22 @@ def extra_config2(ctx):
     g = torch.Generator(device=dev).manual_seed(0)
     res = []
 
-    def t(fn):
+    def t(fn, reps=7):
+        """median of per-repetition CUDA-event times, L2 flushed before each (the operators allocate their outputs, as the
+        reference's do: a repetition that had to go to cudaMalloc shows the host stall between its two events -- the median
+        drops it)"""
         for _ in range(2):
             fn()
-        ms, _ = ctx.timed(fn, 5)
-        return ms / 5
+        ts = []
+        for _ in range(reps):
+            ctx.flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        return float(np.median(ts))
 
     for B in (8, 128):
         cur = (torch.randn(B, 8192, 3, device=dev, generator=g) * torch.tensor([20., 1., 20.], device=dev)).contiguous()
@@ -492,12 +503,18 @@ def extra_config2(ctx):
     ms = t(lambda: _ext.group_points(feats, idx))
     alg = 4 * B * (S * K + C * S * K + C * N)
     res.append(dict(op="group_big", B=B, C=C, N=N, S=S, K=K, ms=ms, gbs=alg / ms / 1e6, frac_hbm=alg / ms / 1e6 / hbm_peak))
+    # context for the HBM fractions: a write-only fill and a copy of the same 1.07 GB, timed the same way
+    out_elems = B * C * S * K
+    dst, srcb = torch.empty(out_elems, device=dev), torch.empty(out_elems, device=dev)
+    ms_fill, ms_copy = t(lambda: dst.fill_(1.0)), t(lambda: dst.copy_(srcb))
+    live = {"fill_write_only_gbs": 4 * out_elems / ms_fill / 1e6, "copy_read_write_gbs": 8 * out_elems / ms_copy / 1e6}
+    del dst, srcb
     for r in res:
         for k, v in list(r.items()):
             if isinstance(v, float):
                 r[k] = round(v, 5)
     return {"config": "BASELINE config 2: op suite, batch 8 clouds x 8192 points (B = 128: the batch of the full forward)",
-            "hbm_peak_gbs": hbm_peak, "ops": res}
+            "hbm_peak_gbs": hbm_peak, "live_peaks": {k: round(v, 1) for k, v in live.items()}, "ops": res}
 
 
 def extra_config3(ctx, net, h1, h2, pairs=16):

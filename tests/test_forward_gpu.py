@@ -175,3 +175,21 @@ def test_forward_streams_two_in_flight_equal_direct(cuda):
     assert len({id(s) for s in fwd.streams}) == 2 and fwd.count == 6
     for (pose, _ev), want in zip(got, direct):
         assert torch.equal(pose, want)
+
+
+@pytest.mark.parametrize("B,N", [(1, 2048), (2, 4096), (1, 16384)])
+def test_forward_other_cloud_sizes_vs_port(cuda, B, N):
+    """the level sizes are fixed (2048 / 1024 / 256 / 64), the input size is not: N = 2048 (level 1 keeps every point),
+    4096, and the 16 384-point clouds of the training configuration (cluster FPS, brute-force level-1 search) -- fused
+    forward (graph replay) against the travelling port of the reference, same kNN summation order"""
+    from oracle.pwclo_port import Port
+    from pwclonet_pylidarslam_b200 import synthetic as syn
+    net, w = _rand_net(cuda, 21 + B)
+    x1, x2, _ = syn.make_batch(640 + N % 97, B, N)
+    with torch.no_grad():
+        pose, log = net(torch.from_numpy(x1).to(cuda), None, torch.from_numpy(x2).to(cuda), None)
+        want, wlog = Port(w, sum_order=1).forward(x1, x2)
+    te, re_ = C.pose_errors(pose.cpu().numpy(), want.numpy())
+    print(f"B={B} N={N}: translation {te:.2e} m, rotation {re_:.2e} rad")
+    assert te <= C.TOL_TRANSLATION_M and re_ <= C.TOL_ROTATION_RAD
+    np.testing.assert_array_equal(log["point_cloud"].numpy(), wlog["point_cloud"].numpy())
