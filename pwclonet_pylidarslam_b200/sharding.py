@@ -91,11 +91,12 @@ class ForwardStreams:
 def auto_compute_streams(pairs):
     """forwards in flight: the sampling chain of a forward (one SM per cloud, ~1.3 ms whatever the batch) overlaps the layer
     kernels of its neighbours.  Measured on one B200 (profiles/round2_streams_sweep.txt), pairs/s with 1 / 2 / 3 in flight:
-    64 pairs 8 879 / 9 736 / 9 866; 8 pairs 3 333 / 5 198 / 6 044; 1 pair 529 / 1 044 / -.  PWCLO_STREAMS overrides."""
+    64 pairs 8 879 / 9 736 / 9 866; 8 pairs 3 333 / 5 198 / 6 044; 1 pair 529 / 1 044 / -; four in flight were erratic.
+    Three everywhere.  PWCLO_STREAMS overrides."""
     import os
     if os.environ.get("PWCLO_STREAMS"):
         return max(1, int(os.environ["PWCLO_STREAMS"]))
-    return 3 if pairs <= 16 else 2
+    return 3
 
 
 class PosePipeline:
