@@ -15,8 +15,9 @@ warp-refinement forward on a batch of 64 synthetic KITTI-64-beam-shaped frame pa
              memory: every step's H2D copy of the rank's two clouds and D2H read of pose_params inside the timed
              region, the copy of step i+1 overlapping the forward of step i
   roofline   the dominant kernel of the step on rank 0, timed live with CUDA events on the launching stream
-  cpu_baseline  the oracle port of the reference forward (oracle/pwclo_port.py, validated bit-exact
-             against the unmodified reference) on this box's host cores, bounded sample (N = 1 only)
+  cpu_baseline  the unmodified reference python model on this box's host cores (staged copy in baseline/_ref; its three
+             CUDA-only native ops served by oracle/pointnet2_cpu.c), else the oracle port of the same forward
+             (oracle/pwclo_port.py, bit-exact against the reference); bounded sample (N = 1 only)
   extra keys (never the headline):
     weak     N > 1: replicas with 64 pairs PER GPU (what round 1 reported)
     latency  N = 1: one forward at 1 / 8 / 64 pairs, CUDA graph replay and launch-by-launch
@@ -187,21 +188,44 @@ def host_info():
 
 
 def cpu_reference(weights, steps, warmup, pairs_per_step=1):
-    """The reference forward on the host cores: oracle port with the reference's own (materialising,
-    torch.topk) kNN formulation and all host threads.  Returns (pairs/s, ms/step, description)."""
-    from oracle.pwclo_port import Port
+    """The reference forward on the host cores, all host threads.  Preferred: the UNMODIFIED reference python model
+    (slam/models/PWCLONet/pwclo_net.py:109-207, read from /root/reference or from the copy staged for the GPU box in
+    baseline/_ref), in eval() under no_grad; its three native ops exist for CUDA only (EXT/src/sampling.cpp:34 "CPU not
+    supported"), so they are served by the C restatement oracle/pointnet2_cpu.c.  Fallback when the reference python is
+    not there: the oracle port of the same forward (bit-identical outputs, tests/test_oracle_cpu.py).
+    Returns (pairs/s, ms/step, sample description, kind, what)."""
     from pwclonet_pylidarslam_b200 import synthetic as syn
     torch.set_num_threads(os.cpu_count() or 1)
-    port = Port(weights, knn_impl="torch")
     x1, x2, _ = syn.make_batch(0, pairs_per_step, N_POINTS)
+    fn = None
+    try:
+        from oracle import ref_shim
+        if ref_shim.available():
+            net = ref_shim.load_reference()
+            net.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+            net.eval()
+            a, b = torch.from_numpy(x1), torch.from_numpy(x2)
+            fn = lambda: net(a, None, b, None)                                       # noqa: E731
+            kind = "reference"
+            what = ("unmodified reference python model (PWCLONet.forward) on CPU; its CUDA-only native ops (FPS, gather, "
+                    "group) served by the C restatement oracle/pointnet2_cpu.c")
+    except Exception as e:       # a broken staging must not cost the run: the port computes the same numbers
+        print(f"reference python not usable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+        fn = None
+    if fn is None:
+        from oracle.pwclo_port import Port
+        port = Port(weights, knn_impl="torch")
+        fn = lambda: port.forward(x1, x2)                                            # noqa: E731
+        kind, what = "port", "oracle port of the reference forward (materialising torch.topk kNN as in the reference)"
     with torch.no_grad():
         for _ in range(warmup):
-            port.forward(x1, x2)
+            fn()
         t0 = time.perf_counter()
         for _ in range(steps):
-            port.forward(x1, x2)
+            fn()
         dt = time.perf_counter() - t0
-    return pairs_per_step * steps / dt, dt / steps * 1e3, f"{steps} forwards of {pairs_per_step} pair(s), N={N_POINTS}, after {warmup} warm-up"
+    sample = f"{steps} forwards of {pairs_per_step} pair(s), N={N_POINTS}, after {warmup} warm-up"
+    return pairs_per_step * steps / dt, dt / steps * 1e3, sample, kind, what
 
 
 def run_reference(args, rank):
@@ -212,15 +236,16 @@ def run_reference(args, rank):
         return
     w = make_weights()
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    v, ms, sample = cpu_reference(w, steps, warmup)
+    v, ms, sample, kind, what = cpu_reference(w, steps, warmup)
     cores = os.cpu_count() or 1
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "PWCLO-Net inference forward, 8192-point synthetic KITTI-64-beam frame pairs, "
-                                   "reference CPU path (oracle port of the reference forward; the reference's CUDA "
-                                   "extension has no CPU path), bounded sample: 1 pair of the 64-pair batch per step"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "host": host_info()},
+                                   "reference CPU path, bounded sample: 1 pair of the 64-pair batch per step",
+                       "implementation": what},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "what": what,
+                             "host": host_info()},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -830,8 +855,8 @@ def main():
                 return {k: m[k] for k in ("value", "ms_per_step", "tf32", "graphed")}
             guarded("train_strict_fp32", strict)
     if world == 1 and not args.no_cpu_baseline and rank == 0:
-        v, ms, sample = cpu_reference(weights, 5, 1)
-        put("cpu_baseline", {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+        v, ms, sample, kind, what = cpu_reference(weights, 5, 1)
+        put("cpu_baseline", {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind, "what": what,
                              "sample": sample, "ms_per_pair": ms, "host": host_info()})
     dog.cancel()
     emit()
