@@ -415,6 +415,13 @@ def rooflines_from(per_kernel, per_work):
         t = traffic_tab.get(fam)
         return (t["dram_bytes_per_launch"], traffic_src) if t else (None, None)
 
+    def ncu_util(name):
+        """pipe utilisation of the kernel family from the committed ncu capture (never measured by bench.py itself)"""
+        fam = "pwclo_knn" if name.startswith("pwclo_knn") else name.replace("_prefix", "")
+        t = traffic_tab.get(fam) or {}
+        keys = ("tensor_pipe_active_pct", "issue_active_pct", "sm_throughput_pct")
+        return {k: t[k] for k in keys if k in t} or None
+
     def roof_of(name):
         """achieved = algorithmic bytes (or MLP flops) of all launches of this kernel / their summed duration"""
         ms = sum(per_kernel[name])
@@ -424,13 +431,14 @@ def rooflines_from(per_kernel, per_work):
             ach = fl / (ms * 1e-3) / 1e12
             return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
                     "frac": ach / tf_peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)",
-                    "traffic_source": tsrc, "peak_kind": peak_kind + " (cuBLAS bf16 sustained)",
+                    "traffic_source": tsrc, "ncu": ncu_util(name), "peak_kind": peak_kind + " (cuBLAS bf16 sustained)",
                     "ms_per_step": ms, "launches_per_step": len(per_kernel[name]),
-                    "note": "fp32-accurate split product (tf32 + 2 bf16 correction MMAs: 8 tcgen05.mma per 32 inputs); "
-                            "flops counted once; the kernels are bound by TMEM operand/accumulator reads, see DESIGN.md"}
+                    "note": "fp32-accurate split product (tf32 + 2 bf16 correction MMAs: 8 tcgen05.mma per 32 inputs, so 0.25 of "
+                            "the bf16 rate is the ceiling of the scheme); flops counted once; one tile per SM alternates between "
+                            "MMAs and row-warp epilogues (TMEM holds one tile's operand planes), see DESIGN.md 7b / 8"}
         ach = by / (ms * 1e-3) / 1e9
         return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)", "traffic_source": tsrc,
+                "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)", "traffic_source": tsrc, "ncu": ncu_util(name),
                 "algorithmic_bytes_per_launch": by / max(1, len(per_kernel[name])),
                 "peak_kind": peak_kind, "ms_per_step": ms, "launches_per_step": len(per_kernel[name]),
                 "note": "algorithmic bytes of SURVEY 8d; this kernel is latency/ALU bound, not HBM bound"}
