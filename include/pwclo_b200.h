@@ -107,7 +107,8 @@ int pwclo_knn(const float *xyz, const float *new_xyz, int B, int N, int S, int K
  * bytes, 16-byte aligned, caller-owned scratch) -- along their widest axis into equal-count strips,
  * every strip along the second-widest axis, plus the strips' ranges along the third -- and each query
  * then visits strips / scans outwards from its own position only as far as its current K-th distance
- * allows.  Falls back to the brute-force kernel when N > 8192 or the workspace is missing / too small.
+ * allows.  Clouds of 8193 .. 16384 points are searched half by half (the halves of the sorted cloud take turns in shared
+ * memory).  Falls back to the brute-force kernel when N > 16384 or the workspace is missing / too small.
  * The workspace is [B] records of pwclo_knn_workspace_bytes(1,N,0) bytes, so the record range of a
  * sub-batch can be passed on its own.
  * pwclo_knn_presort + pwclo_knn_search split the two phases so that several searches against the same

@@ -321,6 +321,8 @@ __device__ __forceinline__ void knn_bitonic(u64* keys, int NP, int kmax, int tid
 __global__ void __launch_bounds__(SORT_THREADS)
 knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, int logL, float* __restrict__ ws,
                    const float* __restrict__ queries, int S, int SP, int* __restrict__ qorder) {
+  const int idbits = NP > 8192 ? 14 : 13;                 // width of the point index inside the in-strip sort key
+  const unsigned idmask = (1u << idbits) - 1u;
   extern __shared__ __align__(16) unsigned char sort_smem[];
   u64* keys = reinterpret_cast<u64*>(sort_smem);
   __shared__ float red[6][32];
@@ -385,7 +387,7 @@ knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, int logL, float
     u64 k2 = ~0ull;
     if (i < N) {
       const unsigned id = (unsigned)keys[i];
-      k2 = ((u64)(i >> logL) << 45) | ((u64)ordered_bits(xyz[id * 3 + axis2]) << 13) | id;
+      k2 = ((u64)(i >> logL) << (32 + idbits)) | ((u64)ordered_bits(xyz[id * 3 + axis2]) << idbits) | id;
     }
     keys[i] = k2;
   }
@@ -395,7 +397,7 @@ knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, int logL, float
     float x = CUDART_INF_F, y = CUDART_INF_F, z = CUDART_INF_F;
     int id = 0;
     if (i < N) {
-      id = (int)((unsigned)keys[i] & 0x1fffu);
+      id = (int)((unsigned)keys[i] & idmask);
       x = xyz[id * 3 + 0]; y = xyz[id * 3 + 1]; z = xyz[id * 3 + 2];
     }
     w[i] = x; w[N4 + i] = y; w[2 * N4 + i] = z;
@@ -406,7 +408,7 @@ knn_presort_kernel(const float* __restrict__ xyz, int N, int NP, int logL, float
     const int axis3 = 3 - axis - axis2;
     float lo3 = CUDART_INF_F, hi3 = -CUDART_INF_F;
     for (int i = (warp << logL) + lane; i < min(N, (warp + 1) << logL); i += 32) {
-      const float v = xyz[(int)((unsigned)keys[i] & 0x1fffu) * 3 + axis3];
+      const float v = xyz[(int)((unsigned)keys[i] & idmask) * 3 + axis3];
       lo3 = fminf(lo3, v); hi3 = fmaxf(hi3, v);
     }
     for (int off = 16; off; off >>= 1) {
@@ -662,6 +664,211 @@ knn_slab_kernel(const float* __restrict__ ws, const int* __restrict__ qorder, co
 
 
 // -------------------------------------------------------------------------------------------------
+// Clouds of 8193 .. 16384 points (the 16 384-point level of the training configuration): the sorted cloud does not fit
+// shared memory (256 KB), its two halves -- strips [0, hs) and [hs, strips), hs = strips / 2 -- do.  A CTA stages half 0,
+// half 1 and half 0 again; a query whose home strip lies in half 0 is searched in pass 0 and finished in pass 1, one whose
+// home strip lies in half 1 starts in pass 1 and is finished in pass 2.  Between the passes the running K-list of every
+// query of the CTA waits in shared memory.  The second visit starts with the bound of the K-th neighbour found at home,
+// so for most queries it ends at the first strip.  Same distances, keys, pruning rule and merge network as
+// knn_slab_kernel: bit-identical to the brute-force kernel.
+// -------------------------------------------------------------------------------------------------
+constexpr int KNN_MAX_N2 = 16384;
+constexpr int KNN2_Q_PER_CTA = 256;
+
+template <int SUM_ORDER>
+__global__ void __launch_bounds__(1024)
+knn_slab2_kernel(const float* __restrict__ ws, const float* __restrict__ new_xyz, int N, int S, int K, int q_per_cta,
+                 const float* __restrict__ warp_qt, float* __restrict__ warped_out, int32_t* __restrict__ idx_out,
+                 float* __restrict__ dist_out) {
+  extern __shared__ __align__(128) unsigned char slab_smem[];
+  constexpr int NH = KNN_MAX_N2 / 2;                 // capacity of a half
+  const int N4 = (N + 3) & ~3;
+  float* sx = reinterpret_cast<float*>(slab_smem);
+  float* sy = sx + NH;
+  float* sz = sy + NH;
+  int* sid = reinterpret_cast<int*>(sz + NH);
+  int* hdr = sid + NH;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float* cand_d = reinterpret_cast<float*>(hdr + KNN_HDR) + (size_t)warp * KNN_BUF;
+  int* cand_i = reinterpret_cast<int*>(reinterpret_cast<float*>(hdr + KNN_HDR) + (size_t)nwarps * KNN_BUF) + (size_t)warp * KNN_BUF;
+  u64* lists = reinterpret_cast<u64*>(reinterpret_cast<float*>(hdr + KNN_HDR) + (size_t)2 * nwarps * KNN_BUF);   // [q_per_cta][32]
+  __shared__ __align__(8) uint64_t bar;
+
+  const int b = blockIdx.y;
+  const float* w = ws + (size_t)b * knn_ws_stride(N);
+  // strip geometry straight from the record in global memory (needed before anything is staged)
+  const int* gh = reinterpret_cast<const int*>(w) + 4 * N4;
+  const int axis = gh[0], axis2 = gh[1], strips = gh[2], logL = gh[3];
+  const int hs = strips >> 1;                         // first strip of half 1
+  const int split = min(hs << logL, N4);              // first sorted position of half 1 (multiple of 32)
+  if (split > NH || N4 - split > NH) __trap();         // cannot happen for N <= 16384 with >= 2 strips; never overrun smem
+  const uint32_t baddr = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(baddr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  new_xyz += (size_t)b * S * 3;
+  PoseQT pose;
+  const bool do_warp = warp_qt != nullptr;
+  if (do_warp) pose = make_pose(warp_qt + (size_t)b * 7);
+  const float* sa1b = reinterpret_cast<const float*>(hdr + 4);
+  const float* sa3lo = sa1b + KNN_MAX_STRIPS + 4;
+  const float* sa3hi = sa3lo + KNN_MAX_STRIPS;
+  const int axis3 = 3 - axis - axis2;
+  const int flush_at = min(32, max(2 * K, 8));
+  const int c_begin = blockIdx.x * q_per_cta, c_end = min(S, c_begin + q_per_cta);
+  const int per_warp = (c_end - c_begin + nwarps - 1) / nwarps;
+  const int w_begin = c_begin + warp * per_warp, w_end = min(c_end, w_begin + per_warp);
+
+  for (int pass = 0; pass < 3; ++pass) {
+    const int half = pass & 1;
+    const int base = half ? split : 0;                       // first sorted position held in shared memory
+    const int count = half ? N4 - split : split;             // multiple of 4
+    __syncthreads();                                         // everybody is done with the previous half
+    if (threadIdx.x == 0) {
+      const uint32_t arr = (uint32_t)count * 4u;
+      const uint32_t bytes = 4u * arr + (pass == 0 ? (uint32_t)(KNN_HDR * sizeof(float)) : 0u);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of the old half before the async writes
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(baddr), "r"(bytes) : "memory");
+      const float* src[4] = {w + base, w + N4 + base, w + 2 * N4 + base, w + 3 * N4 + base};
+      float* dst[4] = {sx, sy, sz, reinterpret_cast<float*>(sid)};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(dst[a])),
+                     "l"(src[a]), "r"(arr), "r"(baddr)
+                     : "memory");
+      if (pass == 0)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(hdr)),
+                     "l"(w + 4 * N4), "r"((uint32_t)(KNN_HDR * sizeof(float))), "r"(baddr)
+                     : "memory");
+    }
+    slab_mbar_wait(&bar, (uint32_t)(pass & 1));
+    const float* ax = sx - base;                             // indexed by the absolute sorted position
+    const float* ay = sy - base;
+    const float* az = sz - base;
+    const int* aid = sid - base;
+    const float* sa = axis2 == 0 ? ax : (axis2 == 1 ? ay : az);
+    const int lo = half ? hs : 0, hi = half ? strips : hs;   // strips of this half
+
+    for (int qpos = w_begin; qpos < w_end; ++qpos) {
+      const int q = qpos;
+      float qx = new_xyz[q * 3 + 0], qy = new_xyz[q * 3 + 1], qz = new_xyz[q * 3 + 2];
+      if (do_warp) warp_point(pose, qx, qy, qz, qx, qy, qz);
+      const float qa1 = axis == 0 ? qx : (axis == 1 ? qy : qz);
+      const float qa = axis2 == 0 ? qx : (axis2 == 1 ? qy : qz);
+      const float qa3 = axis3 == 0 ? qx : (axis3 == 1 ? qy : qz);
+      // home strip over the WHOLE cloud: the last one whose first point is not beyond the query
+      const int home = __popc(__ballot_sync(PWCLO_FULL_MASK, lane >= 1 && lane < strips && sa1b[lane] <= qa1));
+      const bool home_hi = home >= hs;
+      const bool fresh = pass == 0 || (pass == 1 && home_hi);
+      if ((pass == 0 && home_hi) || (pass == 2 && !home_hi)) continue;      // warp-uniform
+      const bool final_pass = pass == 2 || (pass == 1 && !home_hi);
+      if (fresh && do_warp && warped_out != nullptr && lane == 0) {
+        float* o = warped_out + ((size_t)b * S + q) * 3;
+        o[0] = qx; o[1] = qy; o[2] = qz;
+      }
+      auto strip_d1 = [&](int t) -> float {
+        const float d = fmaxf(fmaxf(__fsub_rn(sa1b[t], qa1), __fsub_rn(qa1, sa1b[t + 1])), 0.f);
+        return __fmul_rn(d, d);
+      };
+      auto strip_d13 = [&](int t, float e1) -> float {
+        const float d = fmaxf(fmaxf(__fsub_rn(sa3lo[t], qa3), __fsub_rn(qa3, sa3hi[t])), 0.f);
+        return __fadd_rd(e1, __fmul_rn(d, d));
+      };
+      u64* my_list = lists + (size_t)(qpos - c_begin) * 32;
+      u64 list = fresh ? KNN_INF_KEY : my_list[lane];
+      float bound = CUDART_INF_F;
+      if (!fresh) {
+        const unsigned kv = (unsigned)(shfl_u64(list, K - 1) >> 32);
+        if (kv != (unsigned)(KNN_INF_KEY >> 32)) bound = knn_bound(__uint_as_float(kv));
+      }
+      int t = min(max(home, lo), hi - 1);                 // nearest strip of this half
+      int tl = t - 1, tr = t + 1;
+      float d1 = strip_d1(t);
+      float d13 = strip_d13(t, d1);
+      int cnt = 0;
+      if (d1 <= bound) {
+        while (true) {
+          if (__fmul_rd(d13, KNN_LB_SLACK) <= bound) {
+            const int s_begin = t << logL, s_end = min(N, s_begin + (1 << logL));
+            int lo_b = s_begin, hi_b = s_end;
+            while (lo_b < hi_b) {
+              const int mid = (lo_b + hi_b) >> 1;
+              if (sa[mid] < qa) lo_b = mid + 1; else hi_b = mid;
+            }
+            int left = lo_b - 1, right = lo_b;
+            while (left >= s_begin || right < s_end) {
+              float el = CUDART_INF_F, er = CUDART_INF_F;
+              if (left >= s_begin) { const float d = __fsub_rn(qa, sa[left]); el = __fmul_rn(d, d); }
+              if (right < s_end) { const float d = __fsub_rn(qa, sa[right]); er = __fmul_rn(d, d); }
+              const bool go_left = el <= er;
+              const float e = go_left ? el : er;
+              if (!(__fmul_rd(__fadd_rd(e, d13), KNN_LB_SLACK) <= bound)) break;
+              int pos;
+              bool rv;
+              if (go_left) { pos = left - lane; left -= 32; rv = pos >= s_begin; }
+              else { pos = right + lane; right += 32; rv = pos < s_end; }
+              const int pc = rv ? pos : s_begin;
+              const float dx = __fsub_rn(qx, ax[pc]), dy = __fsub_rn(qy, ay[pc]), dz = __fsub_rn(qz, az[pc]);
+              const float xx = __fmul_rn(dx, dx), yy = __fmul_rn(dy, dy), zz = __fmul_rn(dz, dz);
+              const float d2 = SUM_ORDER == 0 ? __fadd_rn(__fadd_rn(xx, yy), zz) : __fadd_rn(__fadd_rn(xx, zz), yy);
+              const bool pass_c = rv && d2 <= bound;
+              const unsigned mask = __ballot_sync(PWCLO_FULL_MASK, pass_c);
+              if (mask) {
+                if (pass_c) {
+                  const int slot = cnt + __popc(mask & ((1u << lane) - 1u));
+                  cand_d[slot] = d2;
+                  cand_i[slot] = aid[pc];
+                }
+                cnt += __popc(mask);
+                if (cnt >= flush_at) {
+                  __syncwarp();
+                  const u64 ck = lane < cnt ? knn_key(__fsqrt_rn(__fadd_rn(cand_d[lane], 1e-8f)), cand_i[lane]) : KNN_INF_KEY;
+                  const int rest = max(cnt - 32, 0);
+                  float md = 0.f; int mi = 0;
+                  if (lane < rest) { md = cand_d[32 + lane]; mi = cand_i[32 + lane]; }
+                  __syncwarp();
+                  if (lane < rest) { cand_d[lane] = md; cand_i[lane] = mi; }
+                  cnt = rest;
+                  list = knn_merge32(list, ck, lane);
+                  const unsigned kv = (unsigned)(shfl_u64(list, K - 1) >> 32);
+                  if (kv != (unsigned)(KNN_INF_KEY >> 32)) bound = fminf(bound, knn_bound(__uint_as_float(kv)));
+                }
+              }
+            }
+          }
+          if (tl < lo && tr >= hi) break;
+          const float dl = tl >= lo ? strip_d1(tl) : CUDART_INF_F;
+          const float dr = tr < hi ? strip_d1(tr) : CUDART_INF_F;
+          if (tl >= lo && (dl <= dr || tr >= hi)) { t = tl--; d1 = dl; } else { t = tr++; d1 = dr; }
+          if (!(d1 <= bound)) break;
+          d13 = strip_d13(t, d1);
+        }
+      }
+      if (cnt > 0) {
+        __syncwarp();
+        const u64 ck = lane < cnt ? knn_key(__fsqrt_rn(__fadd_rn(cand_d[lane], 1e-8f)), cand_i[lane]) : KNN_INF_KEY;
+        list = knn_merge32(list, ck, lane);
+      }
+      __syncwarp();
+      if (final_pass) {
+        if (lane < K) {
+          const size_t o = ((size_t)b * S + q) * K + lane;
+          idx_out[o] = (int)(unsigned)list;
+          if (dist_out) dist_out[o] = __uint_as_float((unsigned)(list >> 32));
+        }
+      } else {
+        my_list[lane] = list;
+      }
+    }
+  }
+}
+
+
+// -------------------------------------------------------------------------------------------------
 // Small-K variant of the slab search: G = 8 or 16 lanes per query, 32/G queries per warp in lock step.
 // The running list, the candidate queue and the bitonic sort/merge networks are G wide, so a merge
 // costs ~G/32 of the 32-lane version and four (two) queries share every instruction.  Same keys,
@@ -878,7 +1085,7 @@ knn_slab_small_kernel(const float* __restrict__ ws, const float* __restrict__ ne
 }  // namespace pwclo
 
 PWCLO_API size_t pwclo_knn_workspace_bytes(int B, int N, int S) {
-  if (B <= 0 || N <= 0 || S < 0 || N > KNN_MAX_TILE) return 0;
+  if (B <= 0 || N <= 0 || S < 0 || N > KNN_MAX_N2) return 0;
   return (size_t)B * knn_ws_stride(N) * sizeof(float) + (size_t)B * S * sizeof(int);
 }
 
@@ -901,6 +1108,17 @@ static int knn_presort_launch(const float* xyz, int B, int N, int K, float* work
 
 static int knn_search_launch(const float* workspace, const int* qorder, const float* new_xyz, int B, int N, int S, int K,
                              int sum_order, const float* warp_qt, float* warped_out, int32_t* idx, float* dist, cudaStream_t st) {
+  if (N > KNN_MAX_TILE) {      // 8193 .. 16384 points: the two halves of the sorted cloud take turns in shared memory
+    const int warps = 32, q_per_cta = KNN2_Q_PER_CTA;
+    const size_t smem2 = (size_t)4 * (KNN_MAX_N2 / 2) * sizeof(float) + KNN_HDR * sizeof(float) + (size_t)warps * KNN_BUF * 8 +
+                         (size_t)q_per_cta * 32 * sizeof(u64) + 128;
+    auto k2 = sum_order == PWCLO_KNN_SUM_XY_Z ? knn_slab2_kernel<0> : knn_slab2_kernel<1>;
+    cudaError_t e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e != cudaSuccess) return (int)e;
+    k2<<<dim3(ceil_div(S, q_per_cta), B), warps * 32, smem2, st>>>(workspace, new_xyz, N, S, K, q_per_cta, warp_qt, warped_out, idx,
+                                                                    dist);
+    return launch_status();
+  }
   const size_t smem = knn_ws_stride(N) * sizeof(float) + (size_t)SLAB_WARPS * KNN_BUF * 8 + 128;
   // queries per CTA: amortise the shared-memory fill, keep >= ~3 CTAs per SM in flight overall
   int q_per_cta = SLAB_WARPS;
@@ -948,17 +1166,17 @@ PWCLO_API int pwclo_knn_sorted(const float* xyz, const float* new_xyz, int B, in
                                size_t workspace_bytes, void* stream) {
   if (int rc = knn_check(xyz, new_xyz, idx, B, N, S, K, sum_order)) return rc;
   if (B == 0 || S == 0) return PWCLO_OK;
-  if (N > KNN_MAX_TILE || !workspace || workspace_bytes < pwclo_knn_workspace_bytes(B, N, S) || (uintptr_t)workspace % 16 != 0)
+  if (N > KNN_MAX_N2 || !workspace || workspace_bytes < pwclo_knn_workspace_bytes(B, N, S) || (uintptr_t)workspace % 16 != 0)
     return pwclo_knn(xyz, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist, stream);
   cudaStream_t st = (cudaStream_t)stream;
-  int* qorder = S <= 8192 && getenv("PWCLO_KNN_QORDER") ? reinterpret_cast<int*>((float*)workspace + (size_t)B * knn_ws_stride(N)) : nullptr;
+  int* qorder = S <= 8192 && N <= KNN_MAX_TILE && getenv("PWCLO_KNN_QORDER") ? reinterpret_cast<int*>((float*)workspace + (size_t)B * knn_ws_stride(N)) : nullptr;
   if (int rc = knn_presort_launch(xyz, B, N, K, (float*)workspace, new_xyz, S, qorder, st)) return rc;
   return knn_search_launch((const float*)workspace, qorder, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist, st);
 }
 
 PWCLO_API int pwclo_knn_presort(const float* xyz, int B, int N, int K, void* workspace, size_t workspace_bytes, void* stream) {
   if (!xyz || !workspace || B < 0 || N <= 0 || K <= 0 || K > 32) return PWCLO_EINVAL;
-  if (N > KNN_MAX_TILE || B > 65535) return PWCLO_EUNSUPPORTED;
+  if (N > KNN_MAX_N2 || B > 65535) return PWCLO_EUNSUPPORTED;
   if (workspace_bytes < pwclo_knn_workspace_bytes(B, N, 0) || (uintptr_t)workspace % 16 != 0) return PWCLO_EINVAL;
   if (B == 0) return PWCLO_OK;
   return knn_presort_launch(xyz, B, N, K, (float*)workspace, nullptr, 0, nullptr, (cudaStream_t)stream);
@@ -967,7 +1185,7 @@ PWCLO_API int pwclo_knn_presort(const float* xyz, int B, int N, int K, void* wor
 PWCLO_API int pwclo_knn_search(const void* workspace, const float* new_xyz, int B, int N, int S, int K, int sum_order,
                                const float* warp_qt, float* warped_out, int32_t* idx, float* dist, void* stream) {
   if (int rc = knn_check(workspace, new_xyz, idx, B, N, S, K, sum_order)) return rc;
-  if (N > KNN_MAX_TILE) return PWCLO_EUNSUPPORTED;
+  if (N > KNN_MAX_N2) return PWCLO_EUNSUPPORTED;
   if ((uintptr_t)workspace % 16 != 0) return PWCLO_EINVAL;
   if (B == 0 || S == 0) return PWCLO_OK;
   return knn_search_launch((const float*)workspace, nullptr, new_xyz, B, N, S, K, sum_order, warp_qt, warped_out, idx, dist,

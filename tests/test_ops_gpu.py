@@ -188,23 +188,28 @@ def test_knn_vs_oracle_bit_exact(cuda, B, N, S, K, order):
     np.testing.assert_array_equal(got_i.cpu().numpy(), want_i)
 
 
-@pytest.mark.parametrize("B,N,S,K", [(2, 8192, 2048, 32), (3, 2048, 1024, 8), (2, 1000, 333, 6), (2, 100, 64, 32), (1, 64, 7, 4)])
+@pytest.mark.parametrize("B,N,S,K", [(2, 8192, 2048, 32), (3, 2048, 1024, 8), (2, 1000, 333, 6), (2, 100, 64, 32), (1, 64, 7, 4),
+                                     (2, 16384, 2048, 32), (2, 12000, 1500, 16), (1, 8193, 700, 4), (3, 16384, 300, 8)])
 def test_knn_sorted_equals_bruteforce(cuda, B, N, S, K):
-    """the sorted-slab search must be bit-identical to the brute-force kernel (same keys, exact pruning)"""
-    lid = np.stack([synthetic.make_pair(synthetic.SEED_BASE + 60 + i, 8192)["pc2"][:N] for i in range(B)])
+    """the sorted-slab search must be bit-identical to the brute-force kernel (same keys, exact pruning); clouds of more
+    than 8192 points take the two-half kernel (the halves of the sorted cloud take turns in shared memory)"""
+    lid = np.stack([synthetic.make_pair(synthetic.SEED_BASE + 60 + i, max(N, 8192))["pc2"][:N] for i in range(B)])
     rng = np.random.default_rng(3)
     for xyz in (lid, _rand_cloud(rng, B, N), np.round(_rand_cloud(rng, B, N, 3.0))):   # lidar, gaussian, lattice (ties)
         x = _dev(xyz, cuda)
-        q = x[:, :S].contiguous() + 0.0
-        old = _ext.KNN_SORTED
-        try:
-            _ext.KNN_SORTED = True
-            i1, d1 = _ext.knn(x, q, K, return_dist=True)
-            _ext.KNN_SORTED = False
-            i0, d0 = _ext.knn(x, q, K, return_dist=True)
-        finally:
-            _ext.KNN_SORTED = old
-        assert torch.equal(d1, d0) and torch.equal(i1, i0)
+        qs = [x[:, :S].contiguous() + 0.0]
+        if N > 8192:      # queries that are not reference points: shifted into the other half, and far outside the cloud
+            qs += [(x[:, -S:] + torch.tensor([7.0, 0.3, -5.0], device=cuda)).contiguous(), (x[:, :S] * 1.7 + 40.0).contiguous()]
+        for q in qs:
+            old = _ext.KNN_SORTED
+            try:
+                _ext.KNN_SORTED = True
+                i1, d1 = _ext.knn(x, q, K, return_dist=True)
+                _ext.KNN_SORTED = False
+                i0, d0 = _ext.knn(x, q, K, return_dist=True)
+            finally:
+                _ext.KNN_SORTED = old
+            assert torch.equal(d1, d0) and torch.equal(i1, i0)
 
 
 def test_knn_presort_search_split(cuda):
