@@ -614,7 +614,9 @@ def measure_train(ctx, args, steps, warmup, strict_fp32=False):
            torch.from_numpy(q).pin_memory(), torch.from_numpy(t).pin_memory()]
     res = [b.to(dev) for b in pin]
     graphed = not args.no_graph
-    graph_note = "whole step (zero_grad, forward, loss, backward, all-reduce, Adam) replayed as one CUDA graph"
+    graph_note = ("whole step (zero_grad, forward, loss, backward, all-reduce, Adam) replayed as one CUDA graph; the pyramid "
+                  "geometry (sampling chain + neighbour searches) of the NEXT batch replayed as a second graph on its own stream "
+                  "beside it")
     if graphed:
         try:
             tr.capture(res)
@@ -629,13 +631,13 @@ def measure_train(ctx, args, steps, warmup, strict_fp32=False):
         if graphed and not ok:
             graphed, graph_note = False, "CUDA-graph capture failed on another rank; eager step"
             tr.drop_graph()
-    step_fn = tr.train_step_graphed if graphed else tr.train_step
-
-    def step_resident():
-        return step_fn(res)[0]
+    def step_resident():      # graphed: the next batch's coordinates-only work is prefetched on a second stream
+        return (tr.train_step_graphed(res, next_batch=res) if graphed else tr.train_step(res))[0]
 
     def step_e2e():
-        return step_fn(pin if graphed else [b.to(dev, non_blocking=True) for b in pin])[0].cpu()
+        if graphed:
+            return tr.train_step_graphed(pin, next_batch=pin)[0].cpu()
+        return tr.train_step([b.to(dev, non_blocking=True) for b in pin])[0].cpu()
 
     for _ in range(max(3, warmup)):
         step_resident()

@@ -151,7 +151,20 @@ class PWCLONet(nn.Module):
         return self._fused
 
     # -- forward ----------------------------------------------------------------------------------
-    def forward(self, xyz_f1, points_f1, xyz_f2, points_f2, bn_decay=None):
+    def pyramid_geometry(self, xyz_f1, xyz_f2):
+        """The coordinates-only, non-differentiable part of the siamese pyramid for both frames stacked (2B clouds): per
+        level (FPS indices, centres, neighbour indices).  It depends on the input clouds alone -- not on the weights -- so a
+        training loop can compute it for batch i+1 while batch i is still in its backward pass and hand it to
+        forward(..., geoms=...) (training.PWCLONetTrainer does, on a second stream)."""
+        cur = torch.cat((xyz_f1.permute(0, 2, 1), xyz_f2.permute(0, 2, 1)), dim=0).contiguous().detach()
+        geoms = []
+        for psa in (self.psa_1, self.psa_2, self.psa_3, self.psa_4):
+            g = psa.geometry(cur)
+            geoms.append(g)
+            cur = g[1]
+        return geoms
+
+    def forward(self, xyz_f1, points_f1, xyz_f2, points_f2, bn_decay=None, geoms=None):
         no_graph_needed = (not torch.is_grad_enabled()) or (
             not self.eval_autograd and not xyz_f1.requires_grad and not xyz_f2.requires_grad)
         fused_ok = (self.use_fused and not self.training and no_graph_needed
@@ -166,7 +179,7 @@ class PWCLONet(nn.Module):
         else:
             from ..pytorch_utils import deferred_bn_counters
             with deferred_bn_counters():
-                pose, mask1, xyz1_l1 = self._forward_composed(xyz_f1, points_f1, xyz_f2, points_f2)
+                pose, mask1, xyz1_l1 = self._forward_composed(xyz_f1, points_f1, xyz_f2, points_f2, geoms)
         thunks = {
             "embedding_mask": lambda: torch.linalg.norm(
                 F.softmax(mask1.detach().cpu(), dim=2).permute(0, 2, 1), dim=-1, ord=2),
@@ -177,7 +190,7 @@ class PWCLONet(nn.Module):
             log = {k: log[k] for k in thunks}
         return pose, log
 
-    def _forward_composed(self, xyz_f1, points_f1, xyz_f2, points_f2):
+    def _forward_composed(self, xyz_f1, points_f1, xyz_f2, points_f2, geoms=None):
         xyz_f1_t = xyz_f1.permute(0, 2, 1).contiguous()
         xyz_f2_t = xyz_f2.permute(0, 2, 1).contiguous()
         x1, f1, x2, f2 = [xyz_f1_t], [points_f1], [xyz_f2_t], [points_f2]
@@ -186,13 +199,10 @@ class PWCLONet(nn.Module):
         # 16384 -> 2048 sampling is a 2047-round chain on 8 CTAs, twice, otherwise).  The layers keep their per-frame
         # calls: train-mode BatchNorm statistics must be those of one frame's batch, as in the reference.
         Bp = xyz_f1_t.shape[0]
-        geoms, cur = [], torch.cat((xyz_f1_t, xyz_f2_t), dim=0).detach()
         # (the FPS prefix shortcut -- geometry(tie_in=..., return_tie=True) -- is not used: measured, tracking ties costs more
         # on level 1 than the skipped levels give back as soon as one cloud of the batch has a tie; see fused.py)
-        for psa in (self.psa_1, self.psa_2, self.psa_3, self.psa_4):
-            g = psa.geometry(cur)
-            geoms.append(g)
-            cur = g[1]
+        if geoms is None:
+            geoms = self.pyramid_geometry(xyz_f1, xyz_f2)
         for psa, g in zip((self.psa_1, self.psa_2, self.psa_3, self.psa_4), geoms):
             a, b = psa(x1[-1], f1[-1], geom=tuple(t[:Bp] for t in g))
             x1.append(a), f1.append(b)

@@ -176,7 +176,7 @@ class _PWCLONetPredictionModule(nn.Module):
                        scalar_last=cfg.get("scalar_last", False))
         self.pwclonet = PWCLONet(net_cfg)
 
-    def forward(self, data, bn_decay=None):
+    def _clouds(self, data):
         if isinstance(data, dict):
             pcs = []
             for i in range(self.sequence_len):
@@ -192,7 +192,16 @@ class _PWCLONetPredictionModule(nn.Module):
         for pc in pcs:
             xyz.append(pc[:, :self.num_points, :3].permute(0, 2, 1).contiguous())
             feats.append(pc[:, :self.num_points, 3:].permute(0, 2, 1).contiguous() if pc.size(-1) > 3 else None)
-        return self.pwclonet(xyz[0], feats[0], xyz[1], feats[1], bn_decay=bn_decay)
+        return xyz, feats
+
+    def forward(self, data, bn_decay=None, geoms=None):
+        xyz, feats = self._clouds(data)
+        return self.pwclonet(xyz[0], feats[0], xyz[1], feats[1], bn_decay=bn_decay, geoms=geoms)
+
+    def geometry(self, data):
+        """the coordinates-only part of the forward for `data` (PWCLONet.pyramid_geometry): valid for forward(data, geoms=...)"""
+        xyz, _ = self._clouds(data)
+        return self.pwclonet.pyramid_geometry(xyz[0], xyz[1])
 
 
 # ------------------------------------------------------------------ flat arena, all-reduce, Adam
@@ -431,19 +440,19 @@ class PWCLONetTrainer:
                 dist.broadcast(b, src=0)
 
     # ---- one iteration
-    def pred_loss_forward_pass(self, batch):
-        pred, pred_dict = self.prediction_module_(batch)
+    def pred_loss_forward_pass(self, batch, geoms=None):
+        pred, pred_dict = self.prediction_module_(batch, geoms=geoms)
         gt = torch.cat((batch[3], batch[2]), 1)
         loss, log = self.loss_module_(pred, gt)
         return loss, log, pred
 
-    def _step_body(self, batch):
+    def _step_body(self, batch, geoms=None):
         collect = os.environ.get("PWCLO_GRAD_COLLECT", "1") != "0"
         if collect:
             self.arena.detach_grads()
         else:
             self._optimizer.zero_grad()
-        loss, log, pred = self.pred_loss_forward_pass(batch)
+        loss, log, pred = self.pred_loss_forward_pass(batch, geoms)
         loss.backward()
         if collect:
             self.arena.collect_grads()
@@ -459,11 +468,16 @@ class PWCLONetTrainer:
         return out
 
     # ---- the whole step as ONE CUDA graph (the eager step is ~2 500 launches and bound by the host)
-    def capture(self, batch, warmup=3):
+    def capture(self, batch, warmup=3, prefetch=None):
         """Capture zero_grad -> forward -> loss -> backward -> all-reduce -> Adam for batches shaped like
         `batch` (its first four entries are copied into static buffers).  The `warmup` eager steps it runs first
         ARE training steps.  The graph stays valid across steps and learning-rate changes (step counter and lr
-        live in device memory); it is dropped when the BN momentum changes (a captured scalar) or on train(False)."""
+        live in device memory); it is dropped when the BN momentum changes (a captured scalar) or on train(False).
+
+        prefetch (default on, PWCLO_GEO_PREFETCH=0 disables): the coordinates-only part of the forward -- the sampling
+        chain and neighbour searches of the pyramid, ~3 ms of a 17 ms step at 8 pairs x 16 384 points, and independent of
+        the weights -- is captured as its OWN graph; train_step_graphed(batch, next_batch=...) replays it for the next
+        batch on a second stream while the current step is still running."""
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         # Data parallel: the NCCL all-reduce of the gradient arena is captured INSIDE the step graph (NCCL supports stream
         # capture); every rank must capture and replay in lock step.  Measured on 2 B200: 18.0 ms per step against
@@ -471,6 +485,8 @@ class PWCLONetTrainer:
         # teardown with the graph still alive: call drop_graph() (then synchronize + barrier) before
         # destroy_process_group(), see close().  capture_error_mode="thread_local": NCCL's watchdog thread may
         # touch the CUDA API while this thread captures.
+        if prefetch is None:
+            prefetch = os.environ.get("PWCLO_GEO_PREFETCH", "1") != "0"
         self.prediction_module_.train()
         self.loss_module_.train()
         self._static_batch = [b.to(self.device).clone() if torch.is_tensor(b) else b for b in batch[:4]]
@@ -482,29 +498,91 @@ class PWCLONetTrainer:
                 self.train_iter += 1
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
+        kw = {"capture_error_mode": "thread_local"} if multi else {}
+        self._geo_graph, self._geo_cur, self._prefetched, self._copied = None, None, None, None
+        if prefetch:
+            # graph 1: clouds of the NEXT batch (static copies) -> its pyramid geometry (static outputs of the graph)
+            self._geo_stream = torch.cuda.Stream(device=self.device)
+            self._geo_done = torch.cuda.Event()
+            self._geo_in = [self._static_batch[0].clone(), self._static_batch[1].clone()]
+            self._geo_graph = torch.cuda.CUDAGraph()
+            with torch.no_grad():
+                with torch.cuda.graph(self._geo_graph, **kw):
+                    self._geo_out = self.prediction_module_.geometry(self._geo_in)
+                self._geo_graph.replay()
+                torch.cuda.synchronize(self.device)
+                # the step graph reads its geometry from these buffers; a replay of graph 1 must not overwrite them under it
+                self._geo_cur = [tuple(t.clone() for t in g) for g in self._geo_out]
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph, **({"capture_error_mode": "thread_local"} if multi else {})):
-            self._static_out = self._step_body(self._static_batch)
+        with torch.cuda.graph(self._graph, **kw):
+            self._static_out = self._step_body(self._static_batch, self._geo_cur)
         self.train_iter += 1                          # capture executes nothing, but the step below replays it once
         self._graph.replay()
         self._graph_momentum = self._bn_scheduler.last_momentum
         return self._static_out
 
-    def train_step_graphed(self, batch):
+    def _geometry_into_cur(self, batch):
+        """make self._geo_cur hold the pyramid geometry of `batch`: from the prefetch if it was issued for this very
+        batch object, else by replaying the geometry graph now on the current stream"""
+        cur = torch.cuda.current_stream(self.device)
+        if self._prefetched is not None and self._prefetched is batch:
+            cur.wait_event(self._geo_done)
+        else:
+            if self._prefetched is not None:
+                cur.wait_event(self._geo_done)          # an unused prefetch still owns the buffers until it has finished
+            self._geo_in[0].copy_(batch[0], non_blocking=True)
+            self._geo_in[1].copy_(batch[1], non_blocking=True)
+            self._geo_graph.replay()
+        self._prefetched = None
+        torch._foreach_copy_([t for g in self._geo_cur for t in g], [t for g in self._geo_out for t in g])
+        self._copied = torch.cuda.Event()
+        self._copied.record(cur)
+
+    def train_step_graphed(self, batch, next_batch=None):
         """copy the batch into the static buffers and replay the captured step; returns the (static) loss, log
-        and prediction tensors, valid until the next replay"""
+        and prediction tensors, valid until the next replay.  next_batch: the batch the NEXT call will receive (the same
+        object): its coordinates-only work is replayed on a second stream while this step runs."""
         if getattr(self, "_graph", None) is None:
-            return self.capture(batch)
+            self.capture(batch)
+            # fall through: the capture replayed one step on `batch`; continue with the prefetch logic only
+            if next_batch is not None and self._geo_graph is not None:
+                self._issue_prefetch(next_batch)
+            return self._static_out
+        if self._geo_graph is not None:
+            self._geometry_into_cur(batch)
         for dst, src in zip(self._static_batch, batch):
             if torch.is_tensor(dst):
                 dst.copy_(src, non_blocking=True)
         self._graph.replay()
         self.train_iter += 1
+        if next_batch is not None and self._geo_graph is not None:
+            self._issue_prefetch(next_batch)
         return self._static_out
+
+    def _issue_prefetch(self, next_batch):
+        """replay the geometry graph for `next_batch` on the geometry stream.  It overwrites the graph's static outputs, so
+        it must come after this step's copy of them into the step graph's own buffers (`_copied`, recorded right after that
+        copy and BEFORE the step graph on the current stream) -- which lets it run beside the whole step."""
+        ev = getattr(self, "_copied", None)
+        if ev is None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+        gs = self._geo_stream
+        gs.wait_event(ev)
+        with torch.cuda.stream(gs), torch.no_grad():
+            self._geo_in[0].copy_(next_batch[0], non_blocking=True)
+            self._geo_in[1].copy_(next_batch[1], non_blocking=True)
+            self._geo_graph.replay()
+            self._geo_done.record(gs)
+        self._prefetched = next_batch
 
     def drop_graph(self):
         self._graph = None
         self._static_out = None
+        self._geo_graph = None
+        self._geo_out = None
+        self._geo_cur = None
+        self._prefetched = None
 
     def close(self):
         """release the captured step before the process group goes away: a live CUDA graph that holds NCCL work makes

@@ -281,9 +281,12 @@ def test_graphed_step_equals_eager_step(cuda, monkeypatch):
     b.loss_module_.load_state_dict(a.loss_module_.state_dict())
     b._optimizer.load_state_dict(a._optimizer.state_dict())
     for i in range(4):
-        bt = batch if i % 2 == 0 else batch2
+        bt, nxt = (batch, batch2) if i % 2 == 0 else (batch2, batch)
         eager.append(float(a.train_step(bt)[0]))
-        graphed.append(float(b.train_step_graphed(bt)[0]))
+        # steps 0-1 prefetch the next batch's geometry on the second stream, step 2 announces the WRONG next batch (the
+        # prefetch must be discarded), step 3 announces none (geometry replayed in line)
+        graphed.append(float(b.train_step_graphed(bt, next_batch=(nxt if i < 2 else (bt if i == 2 else None)))[0]))
+    assert b._geo_graph is not None
     np.testing.assert_allclose(graphed, eager[6:], rtol=1e-3)   # scatter-add gradients are atomics: run-to-run noise ~1e-5; a real mismatch (e.g. dropout masks) shows at 1e-2
     assert b._optimizer.steps == a._optimizer.steps == 10
     b._optimizer.lr = 5e-4                           # learning-rate changes reach the replayed graph
