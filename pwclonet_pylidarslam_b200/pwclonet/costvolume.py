@@ -35,6 +35,13 @@ class CostVolume(nn.Module):
         """warped_xyz (B,3,S), warped_points (B,C,S), f2_xyz (B,3,N), f2_points (B,C,N) -> (B,mlp[-1],S)"""
         w_t = warped_xyz.permute(0, 2, 1).contiguous()
         f2_t = f2_xyz.permute(0, 2, 1).contiguous()
+        # stage 2's neighbour search and geometry encoding need the warped cloud only: in training they run on the branch
+        # stream beside stage 1
+        branch = pt_utils.on_branch(pt_utils.branch_stream(warped_xyz.device, 1) if self.training else None)
+        with branch:
+            _, idx = pt_utils.knn_point(self.nsample, w_t, w_t)
+            geo2 = self._geometry(warped_xyz, pointutils.grouping_operation(warped_xyz.contiguous(), idx))
+            enc2 = self.mlp_conv_xyz_2(geo2)
         _, idx_q = pt_utils.knn_point(self.nsample_q, f2_t, w_t)
         geo = self._geometry(warped_xyz, pointutils.grouping_operation(f2_xyz.contiguous(), idx_q))
         p_f = warped_points.unsqueeze(3).expand(-1, -1, -1, self.nsample_q)
@@ -42,9 +49,8 @@ class CostVolume(nn.Module):
         x = self.mlp_convs(x)
         wq = F.softmax(self.mlp2_convs(torch.cat((self.mlp_conv_xyz_1(geo), x), dim=1)), dim=3)
         e1 = torch.sum(wq * x, dim=3)
-        _, idx = pt_utils.knn_point(self.nsample, w_t, w_t)
+        branch.join(idx, enc2)
         c_e = pointutils.grouping_operation(e1.contiguous(), idx)
-        geo2 = self._geometry(warped_xyz, pointutils.grouping_operation(warped_xyz.contiguous(), idx))
         n_f = warped_points.unsqueeze(3).expand(-1, -1, -1, self.nsample)
-        wp = F.softmax(self.mlp3_convs(torch.cat((self.mlp_conv_xyz_2(geo2), n_f, c_e), dim=1)), dim=3)
+        wp = F.softmax(self.mlp3_convs(torch.cat((enc2, n_f, c_e), dim=1)), dim=3)
         return torch.sum(wp * c_e, dim=3)

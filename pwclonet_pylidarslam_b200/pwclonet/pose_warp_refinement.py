@@ -4,6 +4,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import PWCLO_utils as pwclo
+from .. import pytorch_utils as pt_utils
 from .costvolume import CostVolume
 from .flowpredictor import FlowPredictor
 from .pose_calculator import PoseCalculator
@@ -41,11 +42,16 @@ class PoseWarpRefinement(nn.Module):
         t_coarse = torch.reshape(t_prev, [B, 3, 1])
         xyz_f1_t = xyz_f1.permute(0, 2, 1).contiguous()
         xyz_prev_t = xyz_f1_prev.permute(0, 2, 1).contiguous()
+        # the mask set-upconv is independent of the feature set-upconv, the warp and the cost volume: in training on the GPU
+        # it runs on a second stream (forward and, through autograd, backward) and joins before the mask predictor
+        branch = pt_utils.on_branch(pt_utils.branch_stream(xyz_f1.device) if self.training else None)
+        with branch:
+            coarse_m = self.setupconv_mask(xyz_f1_t, xyz_prev_t, points_f1, embedding_mask_prev)
         coarse_f = self.setupconv_features(xyz_f1_t, xyz_prev_t, points_f1, points_f1_prev)
-        coarse_m = self.setupconv_mask(xyz_f1_t, xyz_prev_t, points_f1, embedding_mask_prev)
         warped = pwclo.warp(xyz_f1, q_coarse, t_coarse)
         residual = self.cost_volume(warped, points_f1, xyz_f2, points_f2)
         emb = self.flow_predictor_features(points_f1, residual, coarse_f)
+        branch.join(coarse_m)
         mask = coarse_m if self.last_pose_estimation else self.flow_predictor_mask(coarse_m, emb, points_f1)
         q_det, t_det = self.pose_calculator(emb, F.softmax(mask, dim=2))
         q = torch.squeeze(pwclo.mul_point_q(q_det, q_coarse), dim=2)

@@ -14,6 +14,7 @@ Execution:
   * otherwise                -> the autograd composition below (same op order as the reference),
     all sampling / neighbour / grouping ops on the sm_100a kernels.
 """
+import contextlib
 import operator
 import warnings
 from collections.abc import Mapping
@@ -203,12 +204,23 @@ class PWCLONet(nn.Module):
         # on level 1 than the skipped levels give back as soon as one cloud of the batch has a tie; see fused.py)
         if geoms is None:
             geoms = self.pyramid_geometry(xyz_f1, xyz_f2)
+        # The two frames' pyramids are independent until the first cost volume: in training on the GPU the second frame's runs
+        # on the branch stream (pytorch_utils.branch_stream), forward and backward.  Both use the same SharedMLPs, so the
+        # branch leaves their BatchNorm running statistics alone and its updates are applied after the join -- frame 1
+        # first, frame 2 second, as in the reference's sequential calls.
+        from ..pytorch_utils import branch_stream, deferred_running_stats, on_branch
+        stream = branch_stream(xyz_f1.device) if self.training else None
         for psa, g in zip((self.psa_1, self.psa_2, self.psa_3, self.psa_4), geoms):
             a, b = psa(x1[-1], f1[-1], geom=tuple(t[:Bp] for t in g))
             x1.append(a), f1.append(b)
-        for psa, g in zip((self.psa_1, self.psa_2, self.psa_3, self.psa_4), geoms):
-            a, b = psa(x2[-1], f2[-1], geom=tuple(t[Bp:] for t in g))
-            x2.append(a), f2.append(b)
+        branch = on_branch(stream)
+        with branch, (deferred_running_stats() if stream is not None else contextlib.nullcontext()) as later:
+            for psa, g in zip((self.psa_1, self.psa_2, self.psa_3, self.psa_4), geoms):
+                a, b = psa(x2[-1], f2[-1], geom=tuple(t[Bp:] for t in g))
+                x2.append(a), f2.append(b)
+        branch.join(*(x2[1:] + f2[1:]))
+        if later is not None:
+            later.apply()
         X1 = [None] + [x.permute(0, 2, 1).contiguous() for x in x1[1:]]   # [B,3,S] per level 1..4
         X2 = [None] + [x.permute(0, 2, 1).contiguous() for x in x2[1:]]
 

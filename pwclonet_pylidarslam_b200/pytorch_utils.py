@@ -36,7 +36,7 @@ class FusedBNReLUTrain(torch.autograd.Function):
         B, C = x.shape[0], x.shape[1]
         HW = x.numel() // (B * C)
         L = _lib.lib()
-        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None       # running_* may be None: no update
         y = torch.empty_like(x)
         mean = torch.empty(C, dtype=torch.float32, device=x.device)
         invstd = torch.empty(C, dtype=torch.float32, device=x.device)
@@ -47,6 +47,7 @@ class FusedBNReLUTrain(torch.autograd.Function):
                        "bn_relu_train_fwd")
         ctx.save_for_backward(x, weight, bias, mean, invstd)
         ctx.dims = (B, C, HW)
+        FusedBNReLUTrain.last_stats = (mean, invstd, B * HW)
         return y
 
     @staticmethod
@@ -155,6 +156,86 @@ class deferred_bn_counters:
             rec[1] += 1
 
 
+class deferred_running_stats:
+    """Context for a branch that runs CONCURRENTLY with another use of the same modules (the second frame's pyramid shares
+    its SharedMLPs with the first frame's): the train-mode BatchNorm kernels inside it leave the running statistics alone
+    and record their batch statistics instead; apply() performs  running = (1 - momentum) * running + momentum * batch
+    (unbiased variance) for all of them with a few multi-tensor launches -- after the join, i.e. after the other branch's
+    in-kernel updates, which is the reference's order (frame 1, then frame 2)."""
+    active = None
+
+    def __enter__(self):
+        self.records = []
+        self.outer, deferred_running_stats.active = deferred_running_stats.active, self.records
+        return self
+
+    def __exit__(self, *exc):
+        deferred_running_stats.active = self.outer
+        return False
+
+    def apply(self):
+        if not self.records:
+            return
+        with torch.no_grad():
+            rm = [n.running_mean for n, *_ in self.records]
+            rv = [n.running_var for n, *_ in self.records]
+            mom = [float(n.momentum) for n, *_ in self.records]
+            keep = [1.0 - m for m in mom]
+            torch._foreach_mul_(rm, keep)
+            torch._foreach_add_(rm, torch._foreach_mul([mean for _, mean, _, _ in self.records], mom))
+            var = torch._foreach_reciprocal(torch._foreach_mul([i for _, _, i, _ in self.records], [i for _, _, i, _ in self.records]))
+            torch._foreach_sub_(var, [float(n.eps) for n, *_ in self.records])                   # biased batch variance
+            torch._foreach_mul_(var, [m * cnt / max(cnt - 1, 1) for m, (_, _, _, cnt) in zip(mom, self.records)])
+            torch._foreach_mul_(rv, keep)
+            torch._foreach_add_(rv, var)
+        self.records.clear()
+
+
+_BRANCH_STREAMS = {}
+
+
+def branch_stream(device, which=0):
+    """The second CUDA stream of the training composition (one per device): independent branches of the network -- the second
+    frame's pyramid, the mask set-upconv, the second stage's geometry encoding of a cost volume -- run on it beside the main
+    stream, forward and (autograd replays an op's backward on the stream of its forward) backward.  The layers are hundreds of
+    small launches that do not fill the machine one at a time.  `which` selects one of several such streams (a cost volume
+    forks while its caller's own branch may still be running).  Returns None when PWCLO_TRAIN_STREAMS=0 or on the CPU."""
+    if device.type != "cuda" or os.environ.get("PWCLO_TRAIN_STREAMS", "1") == "0":
+        return None
+    key = (device.index if device.index is not None else torch.cuda.current_device(), which)
+    if key not in _BRANCH_STREAMS:
+        _BRANCH_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _BRANCH_STREAMS[key]
+
+
+class on_branch:
+    """with on_branch(stream): ...   forks `stream` from the current one; .join(*tensors) makes the current stream wait for
+    the branch and tells the allocator that the tensors produced there are consumed here.  stream None: plain in-line code."""
+
+    def __init__(self, stream):
+        self.stream = stream
+
+    def __enter__(self):
+        if self.stream is not None:
+            self.main = torch.cuda.current_stream(self.stream.device)
+            self.stream.wait_stream(self.main)
+            self.ctx = torch.cuda.stream(self.stream)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.stream is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self, *tensors):
+        if self.stream is not None:
+            self.main.wait_stream(self.stream)
+            for t in tensors:
+                if torch.is_tensor(t):
+                    t.record_stream(self.main)
+
+
 SKINNY_CONV = os.environ.get("PWCLO_SKINNY_CONV", "1") != "0"
 FUSED_BN_RELU = os.environ.get("PWCLO_FUSED_BN", "1") != "0"
 
@@ -197,8 +278,13 @@ class _Conv(nn.Sequential):
                 y = (SkinnyConv1x1.apply(x, self.conv.weight) if SKINNY_CONV and SkinnyConv1x1.usable(x, self.conv)
                      else self.conv(x))
                 deferred_bn_counters.bump(norm.num_batches_tracked)
-                return FusedBNReLUTrain.apply(y, norm.weight, norm.bias, norm.running_mean, norm.running_var, norm.momentum,
-                                              norm.eps)
+                later = deferred_running_stats.active
+                if later is None:
+                    return FusedBNReLUTrain.apply(y, norm.weight, norm.bias, norm.running_mean, norm.running_var, norm.momentum,
+                                                  norm.eps)
+                out = FusedBNReLUTrain.apply(y, norm.weight, norm.bias, None, None, norm.momentum, norm.eps)
+                later.append((norm,) + FusedBNReLUTrain.last_stats)
+                return out
         return super().forward(x)
 
 
