@@ -255,9 +255,9 @@ def test_trainer_step_and_checkpoint_roundtrip(cuda, tmp_path):
 
 
 def test_graphed_step_equals_eager_step(cuda, monkeypatch):
-    """the captured CUDA graph of the whole step reproduces the eager step: same loss sequence on the same
-    batches (the two dropouts of the pose head draw different masks eagerly and under replay, so they are
-    switched off for this comparison)"""
+    """the captured CUDA graphs (step + prefetched geometry) reproduce the eager step: from identical state, the same loss
+    and the same updated parameters, step after step on alternating batches (the two dropouts of the pose head draw
+    different masks eagerly and under replay, so they are switched off for this comparison)"""
     import torch.nn.functional as F_
     monkeypatch.setattr(F_, "dropout", lambda x, p=0.5, training=True, inplace=False: x)
     from pwclonet_pylidarslam_b200 import synthetic as syn
@@ -272,22 +272,30 @@ def test_graphed_step_equals_eager_step(cuda, monkeypatch):
     a = T.PWCLONetTrainer(cfg)
     b = T.PWCLONetTrainer(cfg)
     b.prediction_module_.load_state_dict(a.prediction_module_.state_dict())
-    eager, graphed = [], []
+    def sync_b_to_a():
+        b.prediction_module_.load_state_dict(a.prediction_module_.state_dict())
+        b.loss_module_.load_state_dict(a.loss_module_.state_dict())
+        b._optimizer.load_state_dict(a._optimizer.state_dict())
+
     for i in range(6):
-        eager.append(float(a.train_step(batch if i % 2 == 0 else batch2)[0]))
-    b.capture(batch, warmup=1)                       # = eager steps 0 (warm-up, batch) ... we redo the sequence below
-    # b has now taken 2 steps on `batch`; restart both from a common state
-    b.prediction_module_.load_state_dict(a.prediction_module_.state_dict())
-    b.loss_module_.load_state_dict(a.loss_module_.state_dict())
-    b._optimizer.load_state_dict(a._optimizer.state_dict())
+        a.train_step(batch if i % 2 == 0 else batch2)
+    b.capture(batch, warmup=1)
+    # Every comparison starts from identical state (a -> b): it checks ONE step (forward through the loss, update through
+    # the parameters), not how fast two trajectories of a chaotic system drift apart under the run-to-run noise of the
+    # scatter-add atomics.  Adam's normalised update may flip on gradient entries that are pure noise: a few lr at most.
+    lr = a._optimizer.lr
     for i in range(4):
         bt, nxt = (batch, batch2) if i % 2 == 0 else (batch2, batch)
-        eager.append(float(a.train_step(bt)[0]))
+        sync_b_to_a()
+        la = float(a.train_step(bt)[0])
         # steps 0-1 prefetch the next batch's geometry on the second stream, step 2 announces the WRONG next batch (the
         # prefetch must be discarded), step 3 announces none (geometry replayed in line)
-        graphed.append(float(b.train_step_graphed(bt, next_batch=(nxt if i < 2 else (bt if i == 2 else None)))[0]))
+        lb = float(b.train_step_graphed(bt, next_batch=(nxt if i < 2 else (bt if i == 2 else None)))[0])
+        dp = (a.arena.param - b.arena.param).abs()
+        print(f"step {i}: eager {la:.6f} graphed {lb:.6f} max |dparam| {float(dp.max()) / lr:.2f} lr, mean {float(dp.mean()) / lr:.4f} lr")
+        assert abs(la - lb) <= 1e-5 * abs(la), (i, la, lb)
+        assert float(dp.max()) <= 3.0 * lr and float(dp.mean()) <= 0.2 * lr, (i, float(dp.max()) / lr, float(dp.mean()) / lr)
     assert b._geo_graph is not None
-    np.testing.assert_allclose(graphed, eager[6:], rtol=1e-3)   # scatter-add gradients are atomics: run-to-run noise ~1e-5; a real mismatch (e.g. dropout masks) shows at 1e-2
     assert b._optimizer.steps == a._optimizer.steps == 10
     b._optimizer.lr = 5e-4                           # learning-rate changes reach the replayed graph
     p0 = b.arena.param.clone()

@@ -31,22 +31,31 @@ torch.manual_seed(0)
 a = T.PWCLONetTrainer(cfg)
 b = T.PWCLONetTrainer(cfg)
 b.prediction_module_.load_state_dict(a.prediction_module_.state_dict())
-eager = [float(a.train_step(batch)[0]) for _ in range(2)]
-b.capture(batch, warmup=1)              # b: 1 warm-up step + 1 replay on `batch` = the same two steps as a
-b.prediction_module_.load_state_dict(a.prediction_module_.state_dict())
-b.loss_module_.load_state_dict(a.loss_module_.state_dict())
-b._optimizer.load_state_dict(a._optimizer.state_dict())
-graphed = []
+def sync_b_to_a():
+    b.prediction_module_.load_state_dict(a.prediction_module_.state_dict())
+    b.loss_module_.load_state_dict(a.loss_module_.state_dict())
+    b._optimizer.load_state_dict(a._optimizer.state_dict())
+
+
+for _ in range(2):
+    a.train_step(batch)
+b.capture(batch, warmup=1)
+# Every comparison starts from IDENTICAL state (a -> b), so it checks one step, not how fast two trajectories of a chaotic
+# system (random-init network, 2-pair BatchNorm, scatter-add atomics) drift apart: the loss (the forward) must agree to
+# 1e-5, the updated parameters to a few learning rates (Adam's normalised update can flip on gradient entries that are
+# pure atomics noise).
+lr = cfg.optimizer_learning_rate
+report = []
 for i in range(4):
     bt = batch if i % 2 == 0 else batch2
-    eager.append(float(a.train_step(bt)[0]))
-    graphed.append(float(b.train_step_graphed(bt)[0]))
-print(f"rank {local}: eager {eager[2:]} graphed {graphed}", flush=True)
-# step 0 starts from identical state: the replayed graph must reproduce the eager loss; afterwards the two runs are separate
-# trajectories of a chaotic system (random-init network, 2-pair BatchNorm) fed by the run-to-run noise of the scatter-add
-# atomics, so the bound widens with the step (observed 2e-4 ... 7e-4)
-for i, tol in enumerate((1e-5, 1e-3, 5e-3, 5e-3)):
-    np.testing.assert_allclose(graphed[i], eager[2 + i], rtol=tol)
+    sync_b_to_a()
+    la = float(a.train_step(bt)[0])
+    lb = float(b.train_step_graphed(bt, next_batch=(batch2 if i % 2 == 0 else batch) if i < 2 else None)[0])
+    dp = (a.arena.param - b.arena.param).abs()
+    report.append((la, lb, float(dp.max()) / lr, float(dp.mean()) / lr))
+    assert abs(la - lb) <= 1e-5 * abs(la), (i, la, lb)
+    assert float(dp.max()) <= 3.0 * lr and float(dp.mean()) <= 0.2 * lr, (i, float(dp.max()) / lr, float(dp.mean()) / lr)
+print(f"rank {local}: (eager loss, graphed loss, max |dparam| / lr, mean |dparam| / lr) per step: {report}", flush=True)
 # both ranks hold the same parameters after data-parallel steps
 p = b.arena.param.clone()
 dist.all_reduce(p, op=dist.ReduceOp.MAX)
