@@ -1,0 +1,29 @@
+"""One eager training step (BASELINE config 5 shape) between cudaProfilerStart / Stop for an ncu launch list."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from pwclonet_pylidarslam_b200 import training as T  # noqa: E402
+
+P, NP = 8, 16384
+dev = torch.device("cuda:0")
+h1, h2 = bench.make_inputs(50, P, P, n_points=NP)
+torch.manual_seed(0)
+tr = T.PWCLONetTrainer(T.PWCLONetTrainerConfig(num_points=NP, device="cuda:0", batch_size=P))
+rng = np.random.default_rng(7)
+q = rng.standard_normal((P, 4)).astype(np.float32) * 0.02 + np.array([1, 0, 0, 0], np.float32)
+q /= np.linalg.norm(q, axis=-1, keepdims=True)
+t = (rng.standard_normal((P, 3)) * np.array([0.05, 0.02, 0.3]) + np.array([0, 0, 1.0])).astype(np.float32)
+batch = [torch.from_numpy(np.ascontiguousarray(h1.transpose(0, 2, 1))).to(dev), torch.from_numpy(np.ascontiguousarray(h2.transpose(0, 2, 1))).to(dev),
+         torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev)]
+for _ in range(2):
+    tr.train_step(batch)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+tr.train_step(batch)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
