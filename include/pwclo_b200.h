@@ -243,6 +243,12 @@ int pwclo_warp_fwd(const float *xyz, const float *q, const float *t, int B, int 
 int pwclo_warp_bwd(const float *xyz, const float *q, const float *grad_out, int B, int N, float *grad_xyz,
                    float *grad_q, float *grad_t, void *stream);
 
+/* Max over the neighbour axis in training (F.max_pool2d(x, [1, K]), P2/pointnet2_modules.py:239-243, :499-506) and its
+ * backward: x [rows, K] -> y [rows], arg uint8 [rows] (first maximum wins, NaN propagates); dx [rows, K] = dy at arg, 0
+ * elsewhere (every element written: no zero-fill needed).  K <= 255. */
+int pwclo_maxpool_lastdim_fwd(const float *x, long long rows, int K, float *y, unsigned char *arg, void *stream);
+int pwclo_maxpool_lastdim_bwd(const float *dy, const unsigned char *arg, long long rows, int K, float *dx, void *stream);
+
 /* Train-mode BatchNorm + ReLU of a shared-MLP layer (P2/pytorch_utils.py:86-167: nn.BatchNorm2d(eps) over
  * (B, S, K) followed by ReLU), forward and backward, two launches each.  x, y, dy, dx: [B, C, HW] contiguous.
  * Forward: batch mean / biased variance per channel (double accumulation), running statistics updated as

@@ -265,6 +265,76 @@ adam_step_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* 
 
 }  // namespace pwclo
 
+// -------------------------------------------------------------------------------------------------
+// Max over the neighbour axis for training (F.max_pool2d(x, [1, K]) of P2/pointnet2_modules.py:239-243, :499-506 and
+// its backward): x [rows, K] contiguous -> y [rows], arg [rows] (first maximum wins, NaN propagates: ATen's rule), and
+// dx [rows, K] = dy at arg, 0 elsewhere.  One thread per row, K consecutive floats per thread (a warp covers one contiguous
+// 128 * K byte region), every dx element written exactly once: no atomics, no zero-fill pass.
+// -------------------------------------------------------------------------------------------------
+namespace pwclo {
+__global__ void maxpool_lastdim_fwd_kernel(const float* __restrict__ x, long long rows, int K, float* __restrict__ y,
+                                           unsigned char* __restrict__ arg) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* xr = x + r * K;
+  float best = xr[0];
+  int bi = 0;
+  if ((K & 3) == 0) {                     // 16-byte loads (rows start on 16-byte boundaries when K % 4 == 0)
+    const float4* x4 = reinterpret_cast<const float4*>(xr);
+    for (int k4 = 0; k4 < (K >> 2); ++k4) {
+      const float4 q = x4[k4];
+      const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (v[i] > best || (v[i] != v[i] && best == best)) { best = v[i]; bi = 4 * k4 + i; }
+    }
+  } else {
+    for (int k = 1; k < K; ++k) {
+      const float v = xr[k];
+      if (v > best || (v != v && best == best)) { best = v; bi = k; }
+    }
+  }
+  y[r] = best;
+  arg[r] = (unsigned char)bi;
+}
+__global__ void maxpool_lastdim_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ arg, long long rows,
+                                           int K, float* __restrict__ dx) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float g = dy[r];
+  const int a = arg[r];
+  float* o = dx + r * K;
+  if ((K & 3) == 0) {
+    float4* o4 = reinterpret_cast<float4*>(o);
+    for (int k4 = 0; k4 < (K >> 2); ++k4) {
+      const int k = 4 * k4;
+      o4[k4] = make_float4(k == a ? g : 0.f, k + 1 == a ? g : 0.f, k + 2 == a ? g : 0.f, k + 3 == a ? g : 0.f);
+    }
+  } else {
+    for (int k = 0; k < K; ++k) o[k] = k == a ? g : 0.f;
+  }
+}
+}  // namespace pwclo
+
+PWCLO_API int pwclo_maxpool_lastdim_fwd(const float* x, long long rows, int K, float* y, unsigned char* arg, void* stream) {
+  if (!x || !y || !arg || rows < 0 || K <= 0 || K > 255) return PWCLO_EINVAL;
+  if (rows == 0) return PWCLO_OK;
+  const long long blocks = (rows + 255) / 256;
+  if (blocks > 2147483647LL) return PWCLO_EUNSUPPORTED;
+  pwclo::maxpool_lastdim_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, K, y, arg);
+  return pwclo::launch_status();
+}
+
+PWCLO_API int pwclo_maxpool_lastdim_bwd(const float* dy, const unsigned char* arg, long long rows, int K, float* dx,
+                                        void* stream) {
+  if (!dy || !arg || !dx || rows < 0 || K <= 0 || K > 255) return PWCLO_EINVAL;
+  if (rows == 0) return PWCLO_OK;
+  const long long blocks = (rows + 255) / 256;
+  if (blocks > 2147483647LL) return PWCLO_EUNSUPPORTED;
+  pwclo::maxpool_lastdim_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, arg, rows, K, dx);
+  return pwclo::launch_status();
+}
+
 PWCLO_API int pwclo_warp_fwd(const float* xyz, const float* q, const float* t, int B, int N, float* out, void* stream) {
   if (!xyz || !q || !t || !out || B < 0 || N < 0) return PWCLO_EINVAL;
   if (B == 0 || N == 0) return PWCLO_OK;

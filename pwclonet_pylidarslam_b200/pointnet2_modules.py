@@ -55,7 +55,7 @@ class PointnetSAModulePWCLONet(nn.Module):
         else:
             x = torch.cat((xyz_diff, grouped_xyz), dim=1)
         x = self.mlp_module(x)
-        return new_xyz, F.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1)
+        return new_xyz, pt_utils.max_over_neighbours(x)
 
 
 class PointnetFPModulePWCLONet(nn.Module):
@@ -82,7 +82,7 @@ class PointnetFPModulePWCLONet(nn.Module):
         else:
             x = self.grouper(xyz1, xyz2, features1)
         x = self.mlp(x)
-        x = F.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1)
+        x = pt_utils.max_over_neighbours(x)
         if features2 is not None:
             x = torch.cat([x, features2], dim=1)
         return self.post_mlp(x.unsqueeze(-1)).squeeze(-1)

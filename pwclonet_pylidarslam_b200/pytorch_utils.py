@@ -125,6 +125,50 @@ class SkinnyConv1x1(torch.autograd.Function):
         return dx, dw
 
 
+class MaxPoolLastDim(torch.autograd.Function):
+    """max over the last axis of [B, C, S, K] -> [B, C, S] on the sm_100a kernels (`pwclo_maxpool_lastdim_fwd/_bwd`): what
+    F.max_pool2d(x, kernel_size=[1, K]).squeeze(-1) computes in the set conv / set upconv (P2/pointnet2_modules.py:239-243,
+    :499-506), same tie rule (first maximum), with a backward that writes every gradient element once (ATen's
+    max_pool_backward_nchw took 40 us per call on these shapes)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        import ctypes
+        from . import _lib
+        x = x.contiguous()
+        K = x.shape[-1]
+        rows = x.numel() // K
+        y = torch.empty(x.shape[:-1], dtype=x.dtype, device=x.device)
+        arg = torch.empty(x.shape[:-1], dtype=torch.uint8, device=x.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().pwclo_maxpool_lastdim_fwd(p(x), rows, K, p(y), p(arg), _lib.stream_ptr()), "maxpool_lastdim_fwd")
+        ctx.save_for_backward(arg)
+        ctx.K = K
+        ctx.mark_non_differentiable(arg)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        import ctypes
+        from . import _lib
+        (arg,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty(tuple(dy.shape) + (ctx.K,), dtype=dy.dtype, device=dy.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(dy.device):
+            _lib.check(_lib.lib().pwclo_maxpool_lastdim_bwd(p(dy), p(arg), dy.numel(), ctx.K, p(dx), _lib.stream_ptr()),
+                       "maxpool_lastdim_bwd")
+        return dx
+
+
+def max_over_neighbours(x):
+    """[B, C, S, K] -> [B, C, S]: the reference's F.max_pool2d(x, kernel_size=[1, K]).squeeze(-1)"""
+    if x.is_cuda and x.dtype == torch.float32 and x.shape[-1] <= 255 and os.environ.get("PWCLO_MAXPOOL", "1") != "0":
+        return MaxPoolLastDim.apply(x)
+    return torch.nn.functional.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1)
+
+
 class deferred_bn_counters:
     """Context: the `num_batches_tracked += 1` of every train-mode BatchNorm executed inside it (93 one-element launches
     per training step of PWCLO-Net) is applied on exit with one multi-tensor add per distinct increment.  Same values as

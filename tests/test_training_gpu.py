@@ -395,3 +395,25 @@ def test_ddp_graphed_step_equals_eager_step(cuda):
                        capture_output=True, text=True, timeout=240, cwd=root)
     out = r.stdout + r.stderr
     assert r.returncode == 0 and "rank 0: OK" in out and "rank 1: OK" in out, out[-3000:]
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 300, 32), (3, 64, 100, 16), (2, 64, 77, 8), (1, 5, 33, 6), (2, 3, 10, 1)])
+def test_max_over_neighbours_matches_torch(cuda, shape):
+    """pwclo_maxpool_lastdim_fwd/_bwd against F.max_pool2d(x, [1, K]) on the same GPU: values, and the gradient routing
+    incl. exact ties (ReLU outputs are full of equal zeros: the first maximum must win, as in ATen) and NaN propagation"""
+    import torch.nn.functional as F_
+    from pwclonet_pylidarslam_b200.pytorch_utils import MaxPoolLastDim
+    g = torch.Generator(device=cuda).manual_seed(sum(shape))
+    x = torch.relu(torch.randn(shape, device=cuda, generator=g))          # ~half the entries are exactly 0
+    x[0, 0, 0] = 0.0                                                      # an all-zero row: K-way tie
+    if shape[-1] > 2:
+        x[-1, -1, -1, 1] = float("nan")
+    up = torch.randn(shape[:-1], device=cuda, generator=g)
+    a = x.clone().requires_grad_(True)
+    b = x.clone().requires_grad_(True)
+    ya = MaxPoolLastDim.apply(a)
+    yb = F_.max_pool2d(b, kernel_size=[1, shape[-1]]).squeeze(-1)
+    assert torch.equal(torch.nan_to_num(ya, nan=-7.0), torch.nan_to_num(yb, nan=-7.0))
+    (ya * up).sum().backward()
+    (yb * up).sum().backward()
+    assert torch.equal(torch.nan_to_num(a.grad, nan=-7.0), torch.nan_to_num(b.grad, nan=-7.0))
