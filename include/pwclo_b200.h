@@ -243,6 +243,13 @@ int pwclo_warp_fwd(const float *xyz, const float *q, const float *t, int B, int 
 int pwclo_warp_bwd(const float *xyz, const float *q, const float *grad_out, int B, int N, float *grad_xyz,
                    float *grad_q, float *grad_t, void *stream);
 
+/* Geometry channels of the cost volume in training (PW/costvolume.py:94-105, :159-169): center [B,3,S], grouped
+ * [B,3,S,K] -> out [B,10,S,K] = (p, g, g - p, sqrt(|g - p|^2 + 1e-20)); backward: grad_center [B,3,S] and grad_grouped
+ * [B,3,S,K] (either may be NULL; both overwritten, no atomics).  One launch each. */
+int pwclo_cost_geometry_fwd(const float *center, const float *grouped, int B, int S, int K, float *out, void *stream);
+int pwclo_cost_geometry_bwd(const float *center, const float *grouped, const float *grad_out, int B, int S, int K,
+                            float *grad_center, float *grad_grouped, void *stream);
+
 /* Max over the neighbour axis in training (F.max_pool2d(x, [1, K]), P2/pointnet2_modules.py:239-243, :499-506) and its
  * backward: x [rows, K] -> y [rows], arg uint8 [rows] (first maximum wins, NaN propagates); dx [rows, K] = dy at arg, 0
  * elsewhere (every element written: no zero-fill needed).  K <= 255. */

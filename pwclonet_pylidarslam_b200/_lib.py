@@ -62,6 +62,8 @@ SIGNATURES = {
     "pwclo_warp_bwd": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
     "pwclo_conv1x1_small": [_vp, _vp, _i, _i, _i, _i, ctypes.c_longlong, _vp, _vp],
     "pwclo_conv1x1_wgrad": [_vp, _vp, _i, _i, _i, ctypes.c_longlong, _vp, _vp, _vp],
+    "pwclo_cost_geometry_fwd": [_vp, _vp, _i, _i, _i, _vp, _vp],
+    "pwclo_cost_geometry_bwd": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "pwclo_maxpool_lastdim_fwd": [_vp, ctypes.c_longlong, _i, _vp, _vp, _vp],
     "pwclo_maxpool_lastdim_bwd": [_vp, _vp, ctypes.c_longlong, _i, _vp, _vp],
     "pwclo_pose_loss": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],

@@ -335,6 +335,89 @@ PWCLO_API int pwclo_maxpool_lastdim_bwd(const float* dy, const unsigned char* ar
   return pwclo::launch_status();
 }
 
+// -------------------------------------------------------------------------------------------------
+// Geometry channels of the cost volume for training (PW/costvolume.py:94-105, :159-169): for a centre p [B,3,S] and its
+// grouped neighbours g [B,3,S,K]:  out [B,10,S,K] = (p, g, g - p, sqrt(|g - p|^2 + 1e-20)), and the gradient of both
+// inputs.  The reference composes tile / sub / square / sum / add / sqrt / cat (7 launches forward, ~12 backward).
+// -------------------------------------------------------------------------------------------------
+namespace pwclo {
+__global__ void cost_geometry_fwd_kernel(const float* __restrict__ p, const float* __restrict__ g, int S, int K,
+                                         long long total, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (b, s, k)
+  if (i >= total) return;
+  const long long SK = (long long)S * K;
+  const long long b = i / SK, sk = i - b * SK;
+  const int s = (int)(sk / K);
+  const float* pb = p + b * 3 * S + s;
+  const float* gb = g + b * 3 * SK + sk;
+  const float px = pb[0], py = pb[S], pz = pb[2 * (long long)S];
+  const float gx = gb[0], gy = gb[SK], gz = gb[2 * SK];
+  const float dx = __fsub_rn(gx, px), dy = __fsub_rn(gy, py), dz = __fsub_rn(gz, pz);
+  const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  float* o = out + b * 10 * SK + sk;
+  o[0] = px; o[SK] = py; o[2 * SK] = pz;
+  o[3 * SK] = gx; o[4 * SK] = gy; o[5 * SK] = gz;
+  o[6 * SK] = dx; o[7 * SK] = dy; o[8 * SK] = dz;
+  o[9 * SK] = __fsqrt_rn(__fadd_rn(n2, 1e-20f));
+}
+// one thread per (b, s): its K neighbours; grad_p is their sum (no atomics), grad_g written once
+__global__ void cost_geometry_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g, const float* __restrict__ go,
+                                         int S, int K, long long points, float* __restrict__ gp, float* __restrict__ gg) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (b, s)
+  if (i >= points) return;
+  const long long SK = (long long)S * K;
+  const long long b = i / S;
+  const int s = (int)(i - b * S);
+  const float* pb = p + b * 3 * S + s;
+  const float px = pb[0], py = pb[S], pz = pb[2 * (long long)S];
+  const float* gb = g + b * 3 * SK + (long long)s * K;
+  const float* ob = go + b * 10 * SK + (long long)s * K;
+  float* ggb = gg ? gg + b * 3 * SK + (long long)s * K : nullptr;
+  float ax = 0.f, ay = 0.f, az = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float dx = __fsub_rn(gb[k], px), dy = __fsub_rn(gb[SK + k], py), dz = __fsub_rn(gb[2 * SK + k], pz);
+    const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    const float e = __fsqrt_rn(__fadd_rn(n2, 1e-20f));
+    const float w = ob[9 * SK + k] / e;                       // d sqrt(n2 + eps) / d d = d / e
+    const float tx = ob[6 * SK + k] + w * dx, ty = ob[7 * SK + k] + w * dy, tz = ob[8 * SK + k] + w * dz;   // via d = g - p
+    if (ggb) {
+      ggb[k] = ob[3 * SK + k] + tx;
+      ggb[SK + k] = ob[4 * SK + k] + ty;
+      ggb[2 * SK + k] = ob[5 * SK + k] + tz;
+    }
+    ax += ob[k] - tx;
+    ay += ob[SK + k] - ty;
+    az += ob[2 * SK + k] - tz;
+  }
+  if (gp) {
+    float* gpb = gp + b * 3 * S + s;
+    gpb[0] = ax; gpb[S] = ay; gpb[2 * (long long)S] = az;
+  }
+}
+}  // namespace pwclo
+
+PWCLO_API int pwclo_cost_geometry_fwd(const float* center, const float* grouped, int B, int S, int K, float* out, void* stream) {
+  if (!center || !grouped || !out || B < 0 || S <= 0 || K <= 0) return PWCLO_EINVAL;
+  const long long total = (long long)B * S * K;
+  if (total == 0) return PWCLO_OK;
+  const long long blocks = (total + 255) / 256;
+  if (blocks > 2147483647LL) return PWCLO_EUNSUPPORTED;
+  pwclo::cost_geometry_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(center, grouped, S, K, total, out);
+  return pwclo::launch_status();
+}
+
+PWCLO_API int pwclo_cost_geometry_bwd(const float* center, const float* grouped, const float* grad_out, int B, int S, int K,
+                                      float* grad_center, float* grad_grouped, void* stream) {
+  if (!center || !grouped || !grad_out || B < 0 || S <= 0 || K <= 0) return PWCLO_EINVAL;
+  const long long points = (long long)B * S;
+  if (points == 0 || (!grad_center && !grad_grouped)) return PWCLO_OK;
+  const long long blocks = (points + 127) / 128;
+  if (blocks > 2147483647LL) return PWCLO_EUNSUPPORTED;
+  pwclo::cost_geometry_bwd_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(center, grouped, grad_out, S, K, points,
+                                                                                     grad_center, grad_grouped);
+  return pwclo::launch_status();
+}
+
 PWCLO_API int pwclo_warp_fwd(const float* xyz, const float* q, const float* t, int B, int N, float* out, void* stream) {
   if (!xyz || !q || !t || !out || B < 0 || N < 0) return PWCLO_EINVAL;
   if (B == 0 || N == 0) return PWCLO_OK;

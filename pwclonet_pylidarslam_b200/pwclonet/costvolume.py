@@ -1,12 +1,48 @@
 """Attentive point-to-patch cost volume, reference PW/costvolume.py:19-190 (same constructor,
 parameter names and forward signature).  This is the autograd / training composition on top of the
 sm_100a kNN + grouping kernels; inference goes through pwclonet_pylidarslam_b200.fused."""
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import pointnet2_utils as pointutils
 from .. import pytorch_utils as pt_utils
+
+
+class CostGeometry(torch.autograd.Function):
+    """(center [B,3,S], grouped [B,3,S,K]) -> [B,10,S,K] = (p, q, q - p, |q - p|) on the sm_100a kernels
+    (`pwclo_cost_geometry_fwd/_bwd`), one launch per direction; PWCLO_COST_GEO=0 keeps the torch composition"""
+
+    @staticmethod
+    def forward(ctx, center, grouped):
+        import ctypes
+        from .. import _lib
+        center, grouped = center.contiguous(), grouped.contiguous()
+        B, _, S, K = grouped.shape
+        out = torch.empty((B, 10, S, K), dtype=grouped.dtype, device=grouped.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(grouped.device):
+            _lib.check(_lib.lib().pwclo_cost_geometry_fwd(p(center), p(grouped), B, S, K, p(out), _lib.stream_ptr()),
+                       "cost_geometry_fwd")
+        ctx.save_for_backward(center, grouped)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        import ctypes
+        from .. import _lib
+        center, grouped = ctx.saved_tensors
+        B, _, S, K = grouped.shape
+        go = go.contiguous()
+        gc = torch.empty_like(center) if ctx.needs_input_grad[0] else None
+        gg = torch.empty_like(grouped) if ctx.needs_input_grad[1] else None
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        with torch.cuda.device(grouped.device):
+            _lib.check(_lib.lib().pwclo_cost_geometry_bwd(p(center), p(grouped), p(go), B, S, K, p(gc), p(gg), _lib.stream_ptr()),
+                       "cost_geometry_bwd")
+        return gc, gg
 
 
 class CostVolume(nn.Module):
@@ -25,6 +61,9 @@ class CostVolume(nn.Module):
     @staticmethod
     def _geometry(center, grouped):
         """10 channels (p, q, q-p, |q-p|) of costvolume.py:94-105 / :159-169"""
+        if (grouped.is_cuda and grouped.dtype == torch.float32 and torch.is_grad_enabled()
+                and os.environ.get("PWCLO_COST_GEO", "1") != "0"):
+            return CostGeometry.apply(center, grouped)
         k = grouped.size(3)
         p = center.unsqueeze(3).expand(-1, -1, -1, k)
         d = grouped - p

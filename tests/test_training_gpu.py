@@ -417,3 +417,28 @@ def test_max_over_neighbours_matches_torch(cuda, shape):
     (ya * up).sum().backward()
     (yb * up).sum().backward()
     assert torch.equal(torch.nan_to_num(a.grad, nan=-7.0), torch.nan_to_num(b.grad, nan=-7.0))
+
+
+@pytest.mark.parametrize("B,S,K", [(2, 300, 6), (3, 64, 32), (1, 1000, 4)])
+def test_cost_geometry_matches_torch_composition(cuda, monkeypatch, B, S, K):
+    """pwclo_cost_geometry_fwd/_bwd against the reference's tile / sub / square / sum / sqrt / cat composition
+    (PW/costvolume.py:94-105): values bit-exact up to the size-3 summation order (1 ulp on the norm channel), both input
+    gradients to 1e-5, incl. the self-neighbour rows where q == p (norm = sqrt(1e-20))"""
+    from pwclonet_pylidarslam_b200.pwclonet.costvolume import CostVolume
+    g = torch.Generator(device=cuda).manual_seed(B + S + K)
+    c0 = torch.randn(B, 3, S, device=cuda, generator=g) * 5
+    q0 = c0.unsqueeze(3) + torch.randn(B, 3, S, K, device=cuda, generator=g)
+    q0[..., 0] = c0                                    # first neighbour = the point itself
+    up = torch.randn(B, 10, S, K, device=cuda, generator=g)
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PWCLO_COST_GEO", flag)
+        c, q = c0.clone().requires_grad_(True), q0.clone().requires_grad_(True)
+        out = CostVolume._geometry(c, q)
+        (out * up).sum().backward()
+        res.append((out.detach(), c.grad, q.grad))
+    (o1, gc1, gq1), (o0, gc0, gq0) = res
+    assert torch.equal(o1[:, :9], o0[:, :9])
+    torch.testing.assert_close(o1[:, 9], o0[:, 9], rtol=2e-7, atol=0)
+    torch.testing.assert_close(gq1, gq0, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(gc1, gc0, rtol=1e-5, atol=1e-4)
