@@ -27,6 +27,35 @@ __device__ __forceinline__ float dist2_ref_fma(float dx, float dy, float dz) {
   return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
+// sm_100a packed fp32 arithmetic (SASS FADD2 / FMUL2 / FFMA2): two independent round-to-nearest operations per
+// instruction -- bit for bit the results of the scalar instructions, half the issue slots.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t f2_sub(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// dist2_ref_fma for two candidates at once: fma(dz,dz, fma(dx,dx, dy*dy)) per half, the reference's contraction order
+__device__ __forceinline__ f32x2_t dist2_ref_fma_x2(f32x2_t dx, f32x2_t dy, f32x2_t dz) {
+  return f2_fma(dz, dz, f2_fma(dx, dx, f2_mul(dy, dy)));
+}
+
 // Pose warp of one point, op-for-op the reference's torch expression tree
 // (PW/PWCLO_utils.py:31-63 with mul_q_point :100-132 and mul_point_q :66-97): every product and
 // sum is a separately rounded fp32 operation, left to right.

@@ -126,21 +126,6 @@ __global__ void __launch_bounds__(LT) set_conv_kernel(const SAArgs a) {
 // memory, and the max over the K neighbours is a log-step shuffle transpose-reduce.  No activation
 // ever touches shared memory; the GEMM-tile kernel above wastes most of its tile on these widths.
 // ------------------------------------------------------------------------------------------------
-// sm_100a packed fp32 FMA (SASS FFMA2): two independent round-to-nearest FMAs per instruction -- the same bits as two
-// fmaf, half the issue slots.  acc = {a0, a1} += {x, x} * {w0, w1}.
-typedef unsigned long long f32x2_t;
-__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
-  f32x2_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {
-  f32x2_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-
 template <int R, int CIN4, int COUT>
 __device__ __forceinline__ void small_layer(const float (&x)[R][CIN4], float (&y)[R][COUT], const float* __restrict__ w,
                                             const float* __restrict__ b) {
@@ -151,21 +136,21 @@ __device__ __forceinline__ void small_layer(const float (&x)[R][CIN4], float (&y
   for (int n = 0; n < COUT; n += 4) {
     const float4 bv = *reinterpret_cast<const float4*>(b + n);
 #pragma unroll
-    for (int r = 0; r < R; ++r) { acc[r][n / 2] = pack2(bv.x, bv.y); acc[r][n / 2 + 1] = pack2(bv.z, bv.w); }
+    for (int r = 0; r < R; ++r) { acc[r][n / 2] = f2_pack(bv.x, bv.y); acc[r][n / 2 + 1] = f2_pack(bv.z, bv.w); }
   }
 #pragma unroll
   for (int k = 0; k < CIN4; ++k) {
     f32x2_t xx[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) xx[r] = pack2(x[r][k], x[r][k]);
+    for (int r = 0; r < R; ++r) xx[r] = f2_pack(x[r][k], x[r][k]);
 #pragma unroll
     for (int n = 0; n < COUT; n += 4) {
       const float4 wv = *reinterpret_cast<const float4*>(w + k * COUT + n);   // one broadcast LDS.128 feeds 2 R FFMA2
-      const f32x2_t w01 = pack2(wv.x, wv.y), w23 = pack2(wv.z, wv.w);
+      const f32x2_t w01 = f2_pack(wv.x, wv.y), w23 = f2_pack(wv.z, wv.w);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        acc[r][n / 2] = ffma2(xx[r], w01, acc[r][n / 2]);
-        acc[r][n / 2 + 1] = ffma2(xx[r], w23, acc[r][n / 2 + 1]);
+        acc[r][n / 2] = f2_fma(xx[r], w01, acc[r][n / 2]);
+        acc[r][n / 2 + 1] = f2_fma(xx[r], w23, acc[r][n / 2 + 1]);
       }
     }
   }
@@ -174,7 +159,7 @@ __device__ __forceinline__ void small_layer(const float (&x)[R][CIN4], float (&y
 #pragma unroll
     for (int n = 0; n < COUT; n += 2) {
       float lo, hi;
-      unpack2(acc[r][n / 2], lo, hi);
+      f2_unpack(acc[r][n / 2], lo, hi);
       y[r][n] = fmaxf(lo, 0.f);
       y[r][n + 1] = fmaxf(hi, 0.f);
     }
