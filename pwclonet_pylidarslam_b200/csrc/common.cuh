@@ -41,6 +41,11 @@ __device__ __forceinline__ f32x2_t f2_sub(f32x2_t a, f32x2_t b) {
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 __device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
   f32x2_t r;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
