@@ -326,7 +326,7 @@ def measure_forward(ctx, net, h1, h2, steps, warmup, pairs_total):
     ctx.barrier()
     in_flight = auto_compute_streams(h1.shape[0])
     if in_flight > 1:
-        # few pairs per GPU: the public streaming path keeps two forwards in flight (sharding.ForwardStreams), so the
+        # the public streaming path keeps several forwards in flight (sharding.ForwardStreams), so the
         # sampling chain of step i+1 (one SM per cloud) runs beside the layers of step i.  K steps are timed as ONE
         # bracket; the L2 flush of every step is enqueued on its own stream (there is no "between" two overlapped steps).
         fwd = ForwardStreams(net, in_flight)
@@ -339,7 +339,7 @@ def measure_forward(ctx, net, h1, h2, steps, warmup, pairs_total):
                 fwd.submit(d1, d2)
             fwd.join()
 
-        streamed(max(3, warmup))
+        streamed(max(3, warmup, 2 * in_flight))       # every stream's graph is captured (first submit) and replayed before timing
         attempts = []
         for attempt in range(2):
             ctx.barrier()
@@ -375,7 +375,7 @@ def measure_forward(ctx, net, h1, h2, steps, warmup, pairs_total):
             ctx.flush.zero_()
             yield pin1, pin2
 
-    for _ in pipe.run(host_batches(3)):
+    for _ in pipe.run(host_batches(max(3, 2 * in_flight))):
         pass
     ctx.barrier()
     s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

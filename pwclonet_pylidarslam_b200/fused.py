@@ -380,7 +380,7 @@ class FusedPWCLONet:
     LEVELS = ((2048, 32), (1024, 32), (256, 16), (64, 16))
 
     # ------------------------------------------------------------------ the whole forward as ONE CUDA graph
-    MAX_GRAPHS = 8
+    MAX_GRAPHS = 32     # (shape, slot) records: six forwards in flight (sharding.ForwardStreams) x a few shapes
     OVERLAP_MAX_CLOUDS = 48
 
     def forward_graphed(self, xyz_f1, xyz_f2, slot=0):

@@ -90,25 +90,26 @@ class ForwardStreams:
 
 def auto_compute_streams(pairs):
     """forwards in flight: the sampling chain of a forward (one SM per cloud, ~1.3 ms whatever the batch) overlaps the layer
-    kernels of its neighbours.  Measured on one B200 (profiles/round2_streams_sweep.txt), pairs/s with 1 / 2 / 3 in flight:
-    64 pairs 8 879 / 9 736 / 9 866; 8 pairs 3 333 / 5 198 / 6 044; 1 pair 529 / 1 044 / -; four in flight were erratic.
-    Three everywhere.  PWCLO_STREAMS overrides."""
+    kernels of its neighbours.  Measured on one B200 (profiles/round2_in_flight_sweep.txt), pairs/s with 2 / 3 / 4 / 6 / 8
+    in flight: 64 pairs 9 811 / 10 013 / 10 128 / 10 129 / 10 149; 8 pairs 5 175 / 6 198 / 6 664 / 7 495 / 7 507;
+    1 pair 1 030 / 1 491 / 1 809 / 2 563 / 2 568.  Six everywhere (each in-flight forward owns a captured graph and its
+    static buffers: ~2 GB at 64 pairs).  PWCLO_STREAMS overrides."""
     import os
     if os.environ.get("PWCLO_STREAMS"):
         return max(1, int(os.environ["PWCLO_STREAMS"]))
-    return 3
+    return 6
 
 
 class PosePipeline:
     """Streaming inference for host-resident batches: the host->device copy of batch i+1 (pinned memory, own copy
     stream, second set of device buffers) overlaps the forward of batch i; the [b,4,7] result returns through a
     pinned buffer.  `run(batches)` yields one host pose tensor per batch, in order; a yielded tensor is valid until
-    `depth` further batches have been submitted.  With few pairs per batch two forwards are in flight on two compute
-    streams (ForwardStreams).  Frame pairs stay independent: this is per-rank plumbing, the sharding across GPUs is
+    `depth` further batches have been submitted.  Several forwards (auto_compute_streams: six) are in flight on their own
+    compute streams (ForwardStreams).  Frame pairs stay independent: this is per-rank plumbing, the sharding across GPUs is
     unchanged."""
 
     def __init__(self, net, pairs, n_points, depth=None, compute_streams=None):
-        """compute_streams: forwards in flight (default: 2 for batches of few pairs, else 1); depth: host / device buffer
+        """compute_streams: forwards in flight (default: auto_compute_streams(pairs)); depth: host / device buffer
         sets (default: compute_streams + 1)"""
         compute_streams = auto_compute_streams(pairs) if compute_streams is None else int(compute_streams)
         depth = compute_streams + 1 if depth is None else max(int(depth), compute_streams + 1)

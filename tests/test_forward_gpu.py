@@ -156,25 +156,29 @@ def test_fused_cache_follows_the_weights(cuda):
         assert net._fused is None
 
 
-def test_forward_streams_two_in_flight_equal_direct(cuda):
-    """sharding.ForwardStreams: forwards submitted back to back on two compute streams (own graph + static buffers per
-    stream) return exactly what one-at-a-time calls return, for inputs that change on every submission"""
+@pytest.mark.parametrize("n", [2, 6])
+def test_forward_streams_in_flight_equal_direct(cuda, n):
+    """sharding.ForwardStreams: forwards submitted back to back on n compute streams (own graph + static buffers per
+    stream; six is the default policy) return exactly what one-at-a-time calls return, for inputs that change on every
+    submission and with every stream's graph replayed at least twice"""
     from pwclonet_pylidarslam_b200 import synthetic as syn
-    from pwclonet_pylidarslam_b200.sharding import ForwardStreams
+    from pwclonet_pylidarslam_b200.sharding import ForwardStreams, auto_compute_streams
     net, _ = _rand_net(cuda, 8)
     ins = []
-    for i in range(6):
+    for i in range(7):
         x1, x2, _ = syn.make_batch(600 + 3 * i, 3, 8192)
         ins.append((torch.from_numpy(x1).to(cuda), torch.from_numpy(x2).to(cuda)))
     with torch.no_grad():
         direct = [net(a, None, b, None)[0].clone() for a, b in ins]
-    fwd = ForwardStreams(net, 2)
-    got = [fwd.submit(a, b) for a, b in ins]
+    fwd = ForwardStreams(net, n)
+    order = [i % len(ins) for i in range(2 * n + 1)]
+    got = [fwd.submit(*ins[i]) for i in order]
     fwd.join()
     torch.cuda.synchronize()
-    assert len({id(s) for s in fwd.streams}) == 2 and fwd.count == 6
-    for (pose, _ev), want in zip(got, direct):
-        assert torch.equal(pose, want)
+    assert len({id(s) for s in fwd.streams}) == n and fwd.count == len(order)
+    for (pose, _ev), i in zip(got, order):
+        assert torch.equal(pose, direct[i])
+    assert auto_compute_streams(3) >= 1
 
 
 @pytest.mark.parametrize("B,N", [(1, 2048), (2, 4096), (1, 16384)])
