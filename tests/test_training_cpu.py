@@ -168,3 +168,27 @@ def test_no_cpu_path_anywhere_in_the_new_rows():
         O.pose_params_to_matrices(torch.zeros(2, 4, 7))
     with pytest.raises(RuntimeError, match="no CPU path"):
         O.convert_to_absolute(torch.zeros(2, 4, 4, dtype=torch.float64))
+
+
+def test_channel_padded_conv_is_the_same_function():
+    """pytorch_utils.conv1x1_aligned (zero-padded input channels so the library picks aligned GEMM kernels in training) is
+    conv(x) with the same input / weight gradients, for Conv2d and Conv1d and for every odd channel count of the model"""
+    import torch.nn as nn
+    from pwclonet_pylidarslam_b200 import pytorch_utils as pt
+    old = pt.PAD_CONV_MIN_POSITIONS
+    pt.PAD_CONV_MIN_POSITIONS = 1
+    try:
+        torch.manual_seed(3)
+        for ci, mod, shape in ((19, nn.Conv2d, (2, 19, 8, 4)), (10, nn.Conv2d, (2, 10, 8, 4)), (67, nn.Conv1d, (2, 67, 16)),
+                               (138, nn.Conv2d, (1, 138, 4, 2)), (64, nn.Conv2d, (2, 64, 4, 4))):
+            conv = mod(ci, 8, 1, bias=False)
+            x = torch.randn(shape, requires_grad=True)
+            y0 = conv(x)
+            g0 = torch.autograd.grad(y0.square().sum(), (x, conv.weight))
+            y1 = pt.conv1x1_aligned(conv, x)
+            g1 = torch.autograd.grad(y1.square().sum(), (x, conv.weight))
+            assert torch.allclose(y0, y1, rtol=1e-6, atol=1e-6)
+            for a, b in zip(g0, g1):
+                assert a.shape == b.shape and torch.allclose(a, b, rtol=1e-5, atol=1e-5)
+    finally:
+        pt.PAD_CONV_MIN_POSITIONS = old
