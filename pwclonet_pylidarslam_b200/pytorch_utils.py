@@ -283,7 +283,7 @@ class on_branch:
 SKINNY_CONV = os.environ.get("PWCLO_SKINNY_CONV", "1") != "0"
 FUSED_BN_RELU = os.environ.get("PWCLO_FUSED_BN", "1") != "0"
 PAD_CONV = os.environ.get("PWCLO_PAD_CONV", "1") != "0"
-PAD_CONV_MIN_POSITIONS = 40000
+PAD_CONV_MIN_POSITIONS = int(os.environ.get("PWCLO_PAD_CONV_MIN", "8192"))
 
 
 def conv1x1_aligned(conv, x):

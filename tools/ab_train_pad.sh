@@ -1,9 +1,10 @@
 #!/bin/bash
-# A/B of the training step: library convolutions with odd input-channel counts as they are (PWCLO_PAD_CONV=0) against
-# zero-padded channels (1)
+# A/B of the training step: compact Hamilton product (PWCLO_HAMILTON_FEW 0 / 16) x channel-padding threshold
 mkdir -p gpurun_out
-for G in 0 1 0 1; do
-  PWCLO_PAD_CONV=$G python bench.py --mode train --steps 20 --warmup 5 2>/dev/null > /tmp/ab_$G.json
-  python -c "import sys,json; d=json.loads([l for l in open('/tmp/ab_$G.json') if l.startswith(chr(123))][0]); print('pad_conv', $G, round(d['value'],1), round(d['ms_per_step'],3), d['loss'])" | tee -a gpurun_out/ab_train_pad.txt
+: > gpurun_out/ab_train_small_ops.txt
+for cfg in "0 40000" "16 40000" "16 8192" "16 2048" "0 40000" "16 8192"; do
+  set -- $cfg
+  PWCLO_HAMILTON_FEW=$1 PWCLO_PAD_CONV_MIN=$2 python bench.py --mode train --steps 20 --warmup 5 2>/dev/null > /tmp/ab.json
+  python -c "import sys,json; d=json.loads([l for l in open('/tmp/ab.json') if l.startswith(chr(123))][0]); print('hamilton_few', $1, 'pad_min', $2, round(d['value'],1), round(d['ms_per_step'],3), d['loss'])" | tee -a gpurun_out/ab_train_small_ops.txt
 done
-PWCLO_PAD_CONV=1 python -m pytest tests/test_training_gpu.py -m gpu -q 2>&1 | tail -3 | tee -a gpurun_out/ab_train_pad.txt
+python -m pytest tests/test_training_gpu.py tests/test_layers_gpu.py -m gpu -q 2>&1 | tail -3 | tee -a gpurun_out/ab_train_small_ops.txt

@@ -38,5 +38,9 @@ for e in prof.key_averages(group_by_input_shape=True):
 rows.sort(reverse=True)
 tot = sum(r[0] for r in rows)
 print(f"total self device time {tot / 1e3:.2f} ms")
-for dt, n, k, shp in rows[:70]:
+print("-- ops (self device time, grouped by input shapes)")
+for dt, n, k, shp in [r for r in rows if r[3] != "[]"][:60]:
     print(f"{dt / 1e3:8.3f} ms {n:4d}x  {k[:44]:44s} {shp}")
+print("-- kernels")
+for dt, n, k, shp in [r for r in rows if r[3] == "[]"][:45]:
+    print(f"{dt / 1e3:8.3f} ms {n:4d}x  {k[:110]}")
