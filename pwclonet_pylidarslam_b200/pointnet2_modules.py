@@ -51,9 +51,9 @@ class PointnetSAModulePWCLONet(nn.Module):
         grouped_xyz = pointnet2_utils.grouping_operation(xyz_flipped, idx)
         xyz_diff = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
         if features is not None:
-            x = torch.cat((xyz_diff, pointnet2_utils.grouping_operation(features, idx)), dim=1)
+            x = pt_utils.cat_for(self.mlp_module, (xyz_diff, pointnet2_utils.grouping_operation(features, idx)))
         else:
-            x = torch.cat((xyz_diff, grouped_xyz), dim=1)
+            x = pt_utils.cat_for(self.mlp_module, (xyz_diff, grouped_xyz))
         x = self.mlp_module(x)
         return new_xyz, pt_utils.max_over_neighbours(x)
 
@@ -78,7 +78,7 @@ class PointnetFPModulePWCLONet(nn.Module):
             g_xyz = pointnet2_utils.grouping_operation(xyz1.transpose(1, 2).contiguous(), idx)
             xyz_diff = g_xyz - xyz2.transpose(1, 2).unsqueeze(-1)
             if self.use_xyz:
-                x = torch.cat((x, xyz_diff), dim=1)
+                x = pt_utils.cat_for(self.mlp, (x, xyz_diff))
         else:
             x = self.grouper(xyz1, xyz2, features1)
         x = self.mlp(x)

@@ -84,7 +84,7 @@ class CostVolume(nn.Module):
         _, idx_q = pt_utils.knn_point(self.nsample_q, f2_t, w_t)
         geo = self._geometry(warped_xyz, pointutils.grouping_operation(f2_xyz.contiguous(), idx_q))
         p_f = warped_points.unsqueeze(3).expand(-1, -1, -1, self.nsample_q)
-        x = torch.cat((geo, p_f, pointutils.grouping_operation(f2_points.contiguous(), idx_q)), dim=1)
+        x = pt_utils.cat_for(self.mlp_convs, (geo, p_f, pointutils.grouping_operation(f2_points.contiguous(), idx_q)))
         x = self.mlp_convs(x)
         wq = F.softmax(self.mlp2_convs(torch.cat((self.mlp_conv_xyz_1(geo), x), dim=1)), dim=3)
         e1 = torch.sum(wq * x, dim=3)

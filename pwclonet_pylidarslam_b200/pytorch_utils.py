@@ -78,11 +78,16 @@ class SkinnyConv1x1(torch.autograd.Function):
     DX = {(8, 8), (8, 16)}          # forward (CI, CO) whose input gradient kernel (CO -> CI) exists
 
     @staticmethod
-    def usable(x, conv):
+    def usable(x, conv, shape=None):
+        """`shape`: the input's shape when `x` is only a tensor of the same device / dtype"""
         w = conv.weight
+        shape = tuple(x.shape if shape is None else shape)
+        n = 1
+        for d in shape:
+            n *= d
         return (x.is_cuda and x.dtype == torch.float32 and conv.bias is None and w.shape[2:].numel() == 1
-                and (w.shape[1], w.shape[0]) in SkinnyConv1x1.FWD and (x.numel() // (x.shape[0] * x.shape[1])) % 4 == 0
-                and x.numel() // x.shape[1] >= 65536)
+                and (w.shape[1], w.shape[0]) in SkinnyConv1x1.FWD and (n // (shape[0] * shape[1])) % 4 == 0
+                and n // shape[1] >= 65536)
 
     @staticmethod
     def forward(ctx, x, w):
@@ -286,22 +291,53 @@ PAD_CONV = os.environ.get("PWCLO_PAD_CONV", "1") != "0"
 PAD_CONV_MIN_POSITIONS = int(os.environ.get("PWCLO_PAD_CONV_MIN", "8192"))
 
 
+def conv_pad_channels(conv, positions):
+    """zero channels conv1x1_aligned appends to the input of `conv` (0: the convolution runs as it is)"""
+    ci = conv.in_channels
+    pad = (16 - ci) if ci < 16 else (-ci) % 4
+    if (not PAD_CONV or pad == 0 or conv.bias is not None or conv.weight.shape[2:].numel() != 1
+            or positions < PAD_CONV_MIN_POSITIONS or not isinstance(conv, (nn.Conv2d, nn.Conv1d))):
+        return 0
+    return pad
+
+
 def conv1x1_aligned(conv, x):
     """conv(x) for a bias-free 1x1 convolution whose input-channel count is not a multiple of 4 (the concatenated inputs
     of PWCLO-Net: 19, 35, 67, 138, 74, 42, 10 channels), training on the GPU: input and weight are zero-padded along the
     channel axis (to 16 below 16 channels, else to the next multiple of 4).  The padded channels contribute exact zeros; what
     changes is the library kernel: with an odd leading dimension of W the weight / input gradient GEMMs fall back to
     `..._align1` and `gemmSN_TN` kernels (8 x 67 -> 128 on 131 072 positions: backward 331 us -> 80 us with 68 channels;
-    19 -> 16 on 262 144 positions: 302 -> 87 us; profiles/round2_conv_pad.txt)."""
+    19 -> 16 on 262 144 positions: 302 -> 87 us; profiles/round2_conv_pad.txt).  An input that already carries the zero
+    channels (`cat_for`) is used as it is."""
     ci = conv.in_channels
-    pad = (16 - ci) if ci < 16 else (-ci) % 4
-    if (not PAD_CONV or pad == 0 or conv.bias is not None or conv.weight.shape[2:].numel() != 1
-            or x.numel() // ci < PAD_CONV_MIN_POSITIONS or not isinstance(conv, (nn.Conv2d, nn.Conv1d))):
+    have = x.shape[1] - ci
+    pad = conv_pad_channels(conv, x.numel() // x.shape[1])
+    if have == 0 and pad == 0:
         return conv(x)
+    if have not in (0, pad):
+        raise RuntimeError(f"conv1x1_aligned: input with {x.shape[1]} channels for a convolution of {ci} (+{pad})")
     spec = (0, 0) * (x.dim() - 2) + (0, pad)
-    xp = nn.functional.pad(x, spec)
+    xp = x if have else nn.functional.pad(x, spec)
     wp = nn.functional.pad(conv.weight, spec)
     return nn.functional.conv2d(xp, wp) if x.dim() == 4 else nn.functional.conv1d(xp, wp)
+
+
+def cat_for(consumer, tensors):
+    """torch.cat(tensors, dim=1) as the input of `consumer` (a Conv2d / Conv1d unit of this module or a SharedMLP): when
+    the consumer's first convolution is going to run on zero-padded channels (conv1x1_aligned), the zero channels are
+    written by this concatenation, which saves the padding copy of the largest tensors of the step and its backward"""
+    first = consumer
+    while isinstance(first, nn.Sequential) and not isinstance(first, _Conv):
+        first = next(iter(first.children()))
+    x0 = tensors[0]
+    if isinstance(first, _Conv) and first.fused_train_path(x0):
+        ci = sum(t.shape[1] for t in tensors)
+        shape = (x0.shape[0], ci) + tuple(x0.shape[2:])
+        if ci == first.conv.in_channels and not (SKINNY_CONV and SkinnyConv1x1.usable(x0, first.conv, shape)):
+            pad = conv_pad_channels(first.conv, x0.numel() // x0.shape[1])
+            if pad:
+                tensors = tuple(tensors) + (x0.new_zeros((x0.shape[0], pad) + tuple(x0.shape[2:])),)
+    return torch.cat(tuple(tensors), dim=1)
 
 
 class _BN(nn.Sequential):
@@ -330,25 +366,30 @@ class _Conv(nn.Sequential):
         if activation is not None:
             self.add_module("activation", activation)
 
+    def fused_train_path(self, x):
+        """training on the GPU with BatchNorm + ReLU: conv by torch, then ONE fused BN(train) + ReLU op"""
+        bn = getattr(self, "bn", None)
+        if not (FUSED_BN_RELU and self.training and bn is not None and isinstance(getattr(self, "activation", None), nn.ReLU)
+                and x.is_cuda and x.dtype == torch.float32):
+            return False
+        norm = bn[0]
+        return bool(norm.track_running_stats and norm.momentum is not None and norm.affine)
+
     def forward(self, x):
         """training on the GPU with BatchNorm + ReLU: conv by torch, then ONE fused BN(train) + ReLU op (same
         parameters / buffers / state-dict keys: the nn.BatchNorm module stays the owner of its tensors)"""
-        bn = getattr(self, "bn", None)
-        act = getattr(self, "activation", None)
-        if (FUSED_BN_RELU and self.training and bn is not None and isinstance(act, nn.ReLU) and x.is_cuda
-                and x.dtype == torch.float32):
-            norm = bn[0]
-            if norm.track_running_stats and norm.momentum is not None and norm.affine:
-                y = (SkinnyConv1x1.apply(x, self.conv.weight) if SKINNY_CONV and SkinnyConv1x1.usable(x, self.conv)
-                     else conv1x1_aligned(self.conv, x))
-                deferred_bn_counters.bump(norm.num_batches_tracked)
-                later = deferred_running_stats.active
-                if later is None:
-                    return FusedBNReLUTrain.apply(y, norm.weight, norm.bias, norm.running_mean, norm.running_var, norm.momentum,
-                                                  norm.eps)
-                out = FusedBNReLUTrain.apply(y, norm.weight, norm.bias, None, None, norm.momentum, norm.eps)
-                later.append((norm,) + FusedBNReLUTrain.last_stats)
-                return out
+        if self.fused_train_path(x):
+            norm = self.bn[0]
+            y = (SkinnyConv1x1.apply(x, self.conv.weight) if SKINNY_CONV and SkinnyConv1x1.usable(x, self.conv)
+                 else conv1x1_aligned(self.conv, x))
+            deferred_bn_counters.bump(norm.num_batches_tracked)
+            later = deferred_running_stats.active
+            if later is None:
+                return FusedBNReLUTrain.apply(y, norm.weight, norm.bias, norm.running_mean, norm.running_var, norm.momentum,
+                                              norm.eps)
+            out = FusedBNReLUTrain.apply(y, norm.weight, norm.bias, None, None, norm.momentum, norm.eps)
+            later.append((norm,) + FusedBNReLUTrain.last_stats)
+            return out
         return super().forward(x)
 
 

@@ -192,3 +192,31 @@ def test_channel_padded_conv_is_the_same_function():
                 assert a.shape == b.shape and torch.allclose(a, b, rtol=1e-5, atol=1e-5)
     finally:
         pt.PAD_CONV_MIN_POSITIONS = old
+
+
+def test_concatenation_writes_the_zero_channels_for_its_consumer(monkeypatch):
+    """pytorch_utils.cat_for: when the consumer's first convolution runs on zero-padded channels, the concatenation
+    carries them (no padding copy), conv1x1_aligned takes the input as it is, and the result is conv(cat(...));
+    off the fused training path it is a plain torch.cat"""
+    import torch.nn as nn
+    from pwclonet_pylidarslam_b200 import pytorch_utils as pt
+    torch.manual_seed(5)
+    mlp = pt.SharedMLP([19, 16, 16], bn=True).train()
+    a, b = torch.randn(2, 3, 8, 4), torch.randn(2, 16, 8, 4, requires_grad=True)
+    assert torch.equal(pt.cat_for(mlp, (a, b)), torch.cat((a, b), dim=1))
+    monkeypatch.setattr(pt._Conv, "fused_train_path", lambda self, x: True)
+    monkeypatch.setattr(pt, "PAD_CONV_MIN_POSITIONS", 1)
+    x = pt.cat_for(mlp, (a, b))
+    assert x.shape[1] == 20 and torch.equal(x[:, :19], torch.cat((a, b), dim=1)) and not x[:, 19:].any()
+    conv = next(iter(mlp.children())).conv
+    y = pt.conv1x1_aligned(conv, x)
+    want = conv(torch.cat((a, b), dim=1))
+    assert torch.allclose(y, want, rtol=1e-6, atol=1e-6)
+    g = torch.autograd.grad(y.square().sum(), (b, conv.weight))
+    gw = torch.autograd.grad(want.square().sum(), (b, conv.weight))
+    for u, v in zip(g, gw):
+        assert u.shape == v.shape and torch.allclose(u, v, rtol=1e-5, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        pt.conv1x1_aligned(conv, torch.randn(2, 22, 8, 4))
+    post = pt.SharedMLP([128, 64], bn=True).train()                  # aligned already: nothing appended
+    assert pt.cat_for(post, (torch.randn(2, 64, 8, 1), torch.randn(2, 64, 8, 1))).shape[1] == 128
