@@ -229,8 +229,8 @@ def cpu_reference(weights, steps, warmup, pairs_per_step=1):
 
 
 def run_reference(args, rank):
-    """--impl reference: the CPU implementation of the path (oracle port, checked bit-exact against the unmodified
-    reference) on all host cores; a step is a bounded sample of the workload -- ONE frame pair of the 64-pair batch
+    """--impl reference: the CPU implementation of the path (the unmodified reference python staged in baseline/_ref
+    when present, else the oracle port that is checked bit-exact against it) on all host cores; a step is a bounded sample of the workload -- ONE frame pair of the 64-pair batch
     (0.65 s on 16 cores) -- so that the driver's --steps / --warmup are honoured as given."""
     if rank != 0:
         return
