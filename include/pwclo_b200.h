@@ -256,6 +256,14 @@ int pwclo_cost_geometry_bwd(const float *center, const float *grouped, const flo
 int pwclo_maxpool_lastdim_fwd(const float *x, long long rows, int K, float *y, unsigned char *arg, void *stream);
 int pwclo_maxpool_lastdim_bwd(const float *dy, const unsigned char *arg, long long rows, int K, float *dx, void *stream);
 
+/* Attentive pooling of the cost volume in training (PW/costvolume.py:139-145 and :181-188: F.softmax(w, dim=3), the
+ * product with the grouped features, torch.sum over the neighbour axis) and its backward: w, x [rows, K] contiguous
+ * (rows = B*C*S), out [rows] = sum_k softmax(w[r,:])[k] * x[r,k]; grad_w, grad_x [rows, K] from grad_out [rows] (the
+ * softmax is recomputed from w).  K in {4, 6, 8, 16, 32}, else PWCLO_EUNSUPPORTED.  16-byte aligned tensors. */
+int pwclo_softmax_pool_fwd(const float *w, const float *x, long long rows, int K, float *out, void *stream);
+int pwclo_softmax_pool_bwd(const float *w, const float *x, const float *grad_out, long long rows, int K, float *grad_w,
+                           float *grad_x, void *stream);
+
 /* Train-mode BatchNorm + ReLU of a shared-MLP layer (P2/pytorch_utils.py:86-167: nn.BatchNorm2d(eps) over
  * (B, S, K) followed by ReLU), forward and backward, two launches each.  x, y, dy, dx: [B, C, HW] contiguous.
  * Forward: batch mean / biased variance per channel (double accumulation), running statistics updated as

@@ -66,6 +66,8 @@ SIGNATURES = {
     "pwclo_cost_geometry_bwd": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "pwclo_maxpool_lastdim_fwd": [_vp, ctypes.c_longlong, _i, _vp, _vp, _vp],
     "pwclo_maxpool_lastdim_bwd": [_vp, _vp, ctypes.c_longlong, _i, _vp, _vp],
+    "pwclo_softmax_pool_fwd": [_vp, _vp, ctypes.c_longlong, _i, _vp, _vp],
+    "pwclo_softmax_pool_bwd": [_vp, _vp, _vp, ctypes.c_longlong, _i, _vp, _vp, _vp],
     "pwclo_pose_loss": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
 }
 

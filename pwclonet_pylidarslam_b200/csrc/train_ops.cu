@@ -477,3 +477,132 @@ PWCLO_API int pwclo_pose_loss(const float* pred, const float* gt, const float* s
                                                                                grad_pred, grad_s);
   return pwclo::launch_status();
 }
+
+// -------------------------------------------------------------------------------------------------
+// Attentive pooling of the cost volume in training (PW/costvolume.py:139-145, :181-188):
+//   out[r] = sum_k softmax_k(w[r, :])[k] * x[r, k]        w, x [rows, K] (rows = B*C*S, K neighbours, contiguous)
+// and its backward.  The reference composes softmax / mul / sum (3 launches forward, ~6 backward, four passes over the
+// [B,C,S,K] tensors); here one thread owns a row (K <= 32 values in registers), one pass forward, one pass backward with
+// the softmax recomputed from w (nothing but the inputs is saved).
+//   d out / d x_k = p_k                      d out / d w_k = p_k (x_k - out)
+// -------------------------------------------------------------------------------------------------
+namespace pwclo {
+template <int K>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, float (&v)[K]) {
+  if constexpr (K % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < K / 4; ++i) {
+      const float4 q = reinterpret_cast<const float4*>(p)[i];
+      v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    }
+  } else if constexpr (K % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < K / 2; ++i) {
+      const float2 q = reinterpret_cast<const float2*>(p)[i];
+      v[2 * i] = q.x; v[2 * i + 1] = q.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < K; ++i) v[i] = p[i];
+  }
+}
+template <int K>
+__device__ __forceinline__ void store_row(float* __restrict__ p, const float (&v)[K]) {
+  if constexpr (K % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < K / 4; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else if constexpr (K % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < K / 2; ++i) reinterpret_cast<float2*>(p)[i] = make_float2(v[2 * i], v[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < K; ++i) p[i] = v[i];
+  }
+}
+// softmax of a row in place (w -> p), torch's formula: exp(w - max) / sum
+template <int K>
+__device__ __forceinline__ void softmax_row(float (&w)[K]) {
+  float m = w[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) m = fmaxf(m, w[k]);
+  float z = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) { w[k] = expf(w[k] - m); z += w[k]; }
+#pragma unroll
+  for (int k = 0; k < K; ++k) w[k] = w[k] / z;
+}
+template <int K>
+__global__ void __launch_bounds__(128) softmax_pool_fwd_kernel(const float* __restrict__ w, const float* __restrict__ x,
+                                                                long long rows, float* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float p[K], xv[K];
+  load_row<K>(w + r * K, p);
+  load_row<K>(x + r * K, xv);
+  softmax_row<K>(p);
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc = __fadd_rn(acc, __fmul_rn(p[k], xv[k]));      // mul then sum, as the reference composes it
+  out[r] = acc;
+}
+template <int K>
+__global__ void __launch_bounds__(128) softmax_pool_bwd_kernel(const float* __restrict__ w, const float* __restrict__ x,
+                                                                const float* __restrict__ g, long long rows,
+                                                                float* __restrict__ dw, float* __restrict__ dx) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float p[K], xv[K];
+  load_row<K>(w + r * K, p);
+  load_row<K>(x + r * K, xv);
+  softmax_row<K>(p);
+  float out = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) out = __fadd_rn(out, __fmul_rn(p[k], xv[k]));
+  const float gr = g[r];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float gp = gr * p[k];
+    xv[k] = gp * (xv[k] - out);      // d w_k
+    p[k] = gp;                       // d x_k
+  }
+  store_row<K>(dw + r * K, xv);
+  store_row<K>(dx + r * K, p);
+}
+template <int K>
+static int launch_softmax_pool(const float* w, const float* x, const float* g, long long rows, float* out, float* dw, float* dx,
+                               cudaStream_t st) {
+  const long long blocks = (rows + 127) / 128;
+  if (blocks > 2147483647LL) return PWCLO_EUNSUPPORTED;
+  if (g == nullptr) softmax_pool_fwd_kernel<K><<<(unsigned)blocks, 128, 0, st>>>(w, x, rows, out);
+  else softmax_pool_bwd_kernel<K><<<(unsigned)blocks, 128, 0, st>>>(w, x, g, rows, dw, dx);
+  return launch_status();
+}
+static int dispatch_softmax_pool(const float* w, const float* x, const float* g, long long rows, int K, float* out, float* dw,
+                                 float* dx, cudaStream_t st) {
+  switch (K) {
+    case 4: return launch_softmax_pool<4>(w, x, g, rows, out, dw, dx, st);
+    case 6: return launch_softmax_pool<6>(w, x, g, rows, out, dw, dx, st);
+    case 8: return launch_softmax_pool<8>(w, x, g, rows, out, dw, dx, st);
+    case 16: return launch_softmax_pool<16>(w, x, g, rows, out, dw, dx, st);
+    case 32: return launch_softmax_pool<32>(w, x, g, rows, out, dw, dx, st);
+    default: return PWCLO_EUNSUPPORTED;
+  }
+}
+}  // namespace pwclo
+
+// K in {4, 6, 8, 16, 32} (the neighbour counts of PWCLO-Net's cost volumes); PWCLO_EUNSUPPORTED otherwise (the caller keeps
+// the composed expression).  Tensors 16-byte aligned.
+PWCLO_API int pwclo_softmax_pool_fwd(const float* w, const float* x, long long rows, int K, float* out, void* stream) {
+  if (!w || !x || !out || rows < 0 || K <= 0) return PWCLO_EINVAL;
+  if (rows == 0) return PWCLO_OK;
+  if ((((uintptr_t)w | (uintptr_t)x) & 15) != 0) return PWCLO_EINVAL;
+  return pwclo::dispatch_softmax_pool(w, x, nullptr, rows, K, out, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+PWCLO_API int pwclo_softmax_pool_bwd(const float* w, const float* x, const float* grad_out, long long rows, int K, float* grad_w,
+                                     float* grad_x, void* stream) {
+  if (!w || !x || !grad_out || !grad_w || !grad_x || rows < 0 || K <= 0) return PWCLO_EINVAL;
+  if (rows == 0) return PWCLO_OK;
+  if ((((uintptr_t)w | (uintptr_t)x | (uintptr_t)grad_w | (uintptr_t)grad_x) & 15) != 0) return PWCLO_EINVAL;
+  return pwclo::dispatch_softmax_pool(w, x, grad_out, rows, K, nullptr, grad_w, grad_x, (cudaStream_t)stream);
+}

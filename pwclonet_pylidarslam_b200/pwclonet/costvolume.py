@@ -86,10 +86,8 @@ class CostVolume(nn.Module):
         p_f = warped_points.unsqueeze(3).expand(-1, -1, -1, self.nsample_q)
         x = pt_utils.cat_for(self.mlp_convs, (geo, p_f, pointutils.grouping_operation(f2_points.contiguous(), idx_q)))
         x = self.mlp_convs(x)
-        wq = F.softmax(self.mlp2_convs(torch.cat((self.mlp_conv_xyz_1(geo), x), dim=1)), dim=3)
-        e1 = torch.sum(wq * x, dim=3)
+        e1 = pt_utils.softmax_pool(self.mlp2_convs(torch.cat((self.mlp_conv_xyz_1(geo), x), dim=1)), x)
         branch.join(idx, enc2)
         c_e = pointutils.grouping_operation(e1.contiguous(), idx)
         n_f = warped_points.unsqueeze(3).expand(-1, -1, -1, self.nsample)
-        wp = F.softmax(self.mlp3_convs(torch.cat((enc2, n_f, c_e), dim=1)), dim=3)
-        return torch.sum(wp * c_e, dim=3)
+        return pt_utils.softmax_pool(self.mlp3_convs(torch.cat((enc2, n_f, c_e), dim=1)), c_e)

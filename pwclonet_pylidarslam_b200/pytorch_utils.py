@@ -174,6 +174,51 @@ def max_over_neighbours(x):
     return torch.nn.functional.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1)
 
 
+class SoftmaxPool(torch.autograd.Function):
+    """sum_k softmax(w, dim=-1)[..., k] * x[..., k] on the sm_100a kernels (`pwclo_softmax_pool_fwd/_bwd`): the attentive
+    pooling of the cost volume (PW/costvolume.py:139-145, :181-188) as one pass forward and one backward; the softmax
+    is recomputed from w in the backward, so only the two inputs are kept alive"""
+    KS = (4, 6, 8, 16, 32)
+
+    @staticmethod
+    def forward(ctx, w, x):
+        import ctypes
+        from . import _lib
+        w, x = w.contiguous(), x.contiguous()
+        K = w.shape[-1]
+        out = torch.empty(w.shape[:-1], dtype=w.dtype, device=w.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(w.device):
+            _lib.check(_lib.lib().pwclo_softmax_pool_fwd(p(w), p(x), w.numel() // K, K, p(out), _lib.stream_ptr()),
+                       "softmax_pool_fwd")
+        ctx.save_for_backward(w, x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes
+        from . import _lib
+        w, x = ctx.saved_tensors
+        K = w.shape[-1]
+        g = g.contiguous()
+        dw, dx = torch.empty_like(w), torch.empty_like(x)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(w.device):
+            _lib.check(_lib.lib().pwclo_softmax_pool_bwd(p(w), p(x), p(g), w.numel() // K, K, p(dw), p(dx), _lib.stream_ptr()),
+                       "softmax_pool_bwd")
+        return dw, dx
+
+
+def softmax_pool(w, x):
+    """[B, C, S, K] x 2 -> [B, C, S]: torch.sum(F.softmax(w, dim=3) * x, dim=3) (the reference's expression, used as it is
+    without autograd: the parity path of inference)"""
+    if (w.is_cuda and w.dtype == torch.float32 and x.dtype == torch.float32 and w.shape == x.shape and torch.is_grad_enabled()
+            and (w.requires_grad or x.requires_grad) and w.shape[-1] in SoftmaxPool.KS
+            and os.environ.get("PWCLO_SOFTMAX_POOL", "1") != "0"):
+        return SoftmaxPool.apply(w, x)
+    return torch.sum(nn.functional.softmax(w, dim=3) * x, dim=3)
+
+
 class deferred_bn_counters:
     """Context: the `num_batches_tracked += 1` of every train-mode BatchNorm executed inside it (93 one-element launches
     per training step of PWCLO-Net) is applied on exit with one multi-tensor add per distinct increment.  Same values as

@@ -442,3 +442,40 @@ def test_cost_geometry_matches_torch_composition(cuda, monkeypatch, B, S, K):
     torch.testing.assert_close(o1[:, 9], o0[:, 9], rtol=2e-7, atol=0)
     torch.testing.assert_close(gq1, gq0, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(gc1, gc0, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 300, 6), (3, 16, 64, 32), (1, 32, 1000, 4), (2, 8, 33, 8), (1, 4, 50, 16)])
+def test_softmax_pool_matches_torch_composition(cuda, monkeypatch, shape):
+    """pwclo_softmax_pool_fwd/_bwd (attentive pooling of the cost volume, PW/costvolume.py:139-145, :181-188) against the
+    reference's softmax / mul / sum composition on the same GPU in fp32 and against the same expression in fp64: values and
+    both input gradients within 1e-5 relative + 5e-6 absolute (a few fp32 ulps of the O(10) terms: grad_w = g p (x - out)
+    cancels where x ~ out), and the kernel's distance from the fp64 result is of the size of torch's own fp32 distance;
+    incl. rows with large logits (max-subtraction) and a row of equal logits"""
+    from pwclonet_pylidarslam_b200 import pytorch_utils as pt
+    g = torch.Generator(device=cuda).manual_seed(sum(shape))
+    w0 = torch.randn(shape, device=cuda, generator=g) * 3
+    w0[0, 0, 0] = 2.5                                  # equal logits: uniform weights
+    w0[0, 0, 1] += 80.0                                # large logits: exp() needs the max subtracted
+    x0 = torch.relu(torch.randn(shape, device=cuda, generator=g))
+    up = torch.randn(shape[:-1], device=cuda, generator=g)
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PWCLO_SOFTMAX_POOL", flag)
+        w, x = w0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+        out = pt.softmax_pool(w, x)
+        (out * up).sum().backward()
+        res.append((out.detach(), w.grad, x.grad))
+    w, x = w0.double().requires_grad_(True), x0.double().requires_grad_(True)
+    out = torch.sum(torch.softmax(w, dim=3) * x, dim=3)
+    (out * up.double()).sum().backward()
+    exact = (out.detach(), w.grad, x.grad)
+    for ours, torch32, want, name in zip(res[0], res[1], exact, ("out", "grad_w", "grad_x")):
+        e_ours = (ours.double() - want).abs().max().item()
+        e_torch = (torch32.double() - want).abs().max().item()
+        print(f"softmax_pool {shape} {name}: |ours - fp64| {e_ours:.2e}, |torch fp32 - fp64| {e_torch:.2e}, "
+              f"|ours - torch fp32| {(ours - torch32).abs().max().item():.2e}")
+        torch.testing.assert_close(ours, torch32, rtol=1e-5, atol=5e-6, msg=lambda m: f"{name}: {m}")
+        assert e_ours <= 3 * e_torch + 1e-6, (name, e_ours, e_torch)
+    with torch.no_grad():                              # without autograd: the reference's expression itself
+        monkeypatch.setenv("PWCLO_SOFTMAX_POOL", "1")
+        assert torch.equal(pt.softmax_pool(w0, x0), torch.sum(torch.softmax(w0, dim=3) * x0, dim=3))
