@@ -5,7 +5,6 @@ import os
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import pointnet2_utils as pointutils
 from .. import pytorch_utils as pt_utils
